@@ -29,6 +29,7 @@ Conventions (all mirror the reference):
 """
 from __future__ import annotations
 
+import contextlib
 import itertools
 from typing import List, Sequence, Tuple
 
@@ -39,6 +40,18 @@ F32 = np.float32
 PERIODIC = 'periodic'
 ZG = 'zg'          # ZERO_GRADIENT a.k.a. BOUNDARY
 ZERO = 0.0
+
+
+@contextlib.contextmanager
+def precision(bits: int):
+    """Evaluate the oracle in float64 (bits=64) to obtain an 'exact arithmetic' yardstick for tolerance statements."""
+    global F32
+    old = F32
+    F32 = np.float64 if bits == 64 else np.float32
+    try:
+        yield
+    finally:
+        F32 = old
 
 
 # --------------------------------------------------------------------------------------------------
@@ -572,9 +585,10 @@ def plume_step(v, s, p, dt, vbc, sbc, lower, upper, res, inflow_mask, inflow_rat
     else:
         s_adv = semi_lagrangian_centered(s, sbc, v, vbc, lower, upper, dt)
     s_new = (s_adv + F32(inflow_rate) * inflow_mask).astype(F32)
-    faces = centered_to_faces(s_new, sbc, vbc)
+    # buoyancy = resample(s * (0, 0.1), to=v): scale the centred field first, then average to the faces
+    faces = [centered_to_faces(s_new * F32(buoyancy[c]), sbc, vbc)[c] for c in range(d)]
     v_adv = semi_lagrangian_staggered(v, vbc, v, vbc, res, lower, upper, dt)
-    v_b = [(v_adv[c] + (faces[c] * F32(buoyancy[c])) * F32(dt)).astype(F32) for c in range(d)]
+    v_b = [(v_adv[c] + faces[c] * F32(dt)).astype(F32) for c in range(d)]
     v_new, p_new, info = make_incompressible(v_b, vbc, res, dx, rtol, atol, max_iter, x0=p,
                                              use_matrix_offset=use_matrix_offset, rng=rng, matrix=matrix)
     return v_new, s_new, p_new, info

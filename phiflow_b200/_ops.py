@@ -1,0 +1,316 @@
+"""
+Array-level host API over the C ABI: device layout, conversions from/to the reference's array layout, and one Python
+function per exported entry point.  torch is used for device memory and streams only.
+
+Boundary specs use the same plain encoding as the reference-side tests: a tuple over axes (x, y[, z]) of
+(lower, upper) sides, each 'periodic', 'zg' (ZERO_GRADIENT == BOUNDARY) or a float constant.
+"""
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import PhiGrid, PhiBC, PhiVBC, PhiCgParams, PhiCgResult, PhiPlumeParams, F3
+
+PERIODIC, ZG = 'periodic', 'zg'
+_RESULT_DTYPE = np.dtype([('iterations', np.int32), ('converged', np.int32), ('diverged', np.int32),
+                          ('residual_sq', np.float32), ('tol_sq', np.float32), ('initial_residual_sq', np.float32)])
+
+
+def _kind(side):
+    if side == PERIODIC:
+        return _lib.BC_PERIODIC
+    if side == ZG:
+        return _lib.BC_ZERO_GRADIENT
+    return _lib.BC_CONST
+
+
+def make_bc(spec) -> PhiBC:
+    bc = PhiBC()
+    for a, (lo, hi) in enumerate(spec):
+        bc.lo[a], bc.hi[a] = _kind(lo), _kind(hi)
+        bc.clo[a] = float(lo) if not isinstance(lo, str) else 0.0
+        bc.chi[a] = float(hi) if not isinstance(hi, str) else 0.0
+    return bc
+
+
+def make_vbc(spec, dim) -> PhiVBC:
+    """spec: one boundary spec for all components, or a list of `dim` specs (per-component constants)."""
+    per_comp = spec if isinstance(spec, list) else [spec] * dim
+    vbc = PhiVBC()
+    for c in range(dim):
+        vbc.comp[c] = make_bc(per_comp[c])
+    return vbc
+
+
+def stored_faces(vspec, axis):
+    """(lower stored, upper stored) - PhiML/phiml/math/extrapolation.py:57-62."""
+    spec = vspec[0] if isinstance(vspec, list) else vspec
+    lo, hi = spec[axis]
+    return (lo == ZG or lo == PERIODIC), (hi == ZG)
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("phiflow_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _f3(ts: Sequence[torch.Tensor]):
+    arr = F3()
+    for i in range(3):
+        arr[i] = ts[i].data_ptr() if i < len(ts) else None
+    return arr
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Domain:
+    """Resolution, cell size, batch size and the allocation extents of centred / staggered arrays (include/phicuda.h)."""
+
+    def __init__(self, resolution: Sequence[int], dx: Sequence[float], batch: int = 1, vbc=None, device='cuda'):
+        self.dim = len(resolution)
+        assert self.dim in (2, 3), "only 2-D and 3-D grids"
+        self.res = tuple(int(r) for r in resolution)
+        self.dx = tuple(float(d) for d in dx)
+        self.batch = int(batch)
+        self.device = torch.device(device)
+        self.upper = tuple(stored_faces(vbc, a)[1] if vbc is not None else False for a in range(self.dim))
+        r4 = lambda v: (v + 3) // 4 * 4
+        self.cext = (r4(self.res[0]),) + self.res[1:]
+        self.fext = (r4(self.res[0] + int(self.upper[0])),) + tuple(self.res[a] + int(self.upper[a]) for a in range(1, self.dim))
+        g = PhiGrid()
+        g.dim, g.batch = self.dim, self.batch
+        for a in range(3):
+            g.n[a] = self.res[a] if a < self.dim else 1
+            g.cext[a] = self.cext[a] if a < self.dim else 1
+            g.fext[a] = self.fext[a] if a < self.dim else 1
+            g.dx[a] = self.dx[a] if a < self.dim else 1.0
+        self.grid = g
+        self._ws = None
+        self._result = None
+        self._scratch = None
+
+    # ---- allocation ---------------------------------------------------------------------------------------------
+    def _shape(self, ext):
+        return (self.batch,) + tuple(reversed(ext))
+
+    def alloc_centered(self) -> torch.Tensor:
+        return torch.zeros(self._shape(self.cext), dtype=torch.float32, device=self.device)
+
+    def alloc_faces(self) -> List[torch.Tensor]:
+        return [torch.zeros(self._shape(self.fext), dtype=torch.float32, device=self.device) for _ in range(self.dim)]
+
+    def workspace(self):
+        if self._ws is None:
+            n = _lib.load().phicuda_cg_workspace_bytes(C.byref(self.grid))
+            self._ws = torch.zeros(n, dtype=torch.uint8, device=self.device)
+            self._result = torch.zeros(self.batch * 6, dtype=torch.int32, device=self.device)
+        return self._ws, self._result
+
+    def scratch(self):
+        if self._scratch is None:
+            n = _lib.load().phicuda_plume_scratch_bytes(C.byref(self.grid))
+            self._scratch = torch.zeros(n // 4, dtype=torch.float32, device=self.device)
+        return self._scratch
+
+    # ---- conversions: reference layout (x, y[, z]) <-> device layout (b, [z,] y, x) ------------------------------------
+    def _to_dev(self, a: np.ndarray, ext, offset_axis=None, offset=0) -> torch.Tensor:
+        a = np.asarray(a, dtype=np.float32)
+        if a.ndim == self.dim:
+            a = a[None]
+        assert a.ndim == self.dim + 1 and a.shape[0] in (1, self.batch), f"bad array shape {a.shape}"
+        if a.shape[0] != self.batch:
+            a = np.broadcast_to(a, (self.batch,) + a.shape[1:])
+        t = torch.zeros(self._shape(ext), dtype=torch.float32, device=self.device)
+        src = torch.from_numpy(np.ascontiguousarray(np.transpose(a, (0,) + tuple(range(self.dim, 0, -1)))))
+        idx = [slice(None)]
+        for ax in range(self.dim - 1, -1, -1):               # device axis order: z, y, x
+            start = offset if ax == offset_axis else 0
+            idx.append(slice(start, start + a.shape[1 + ax]))
+        t[tuple(idx)] = src.to(self.device)
+        return t
+
+    def _to_host(self, t: torch.Tensor, shape, offset_axis=None, offset=0) -> np.ndarray:
+        idx = [slice(None)]
+        for ax in range(self.dim - 1, -1, -1):
+            start = offset if ax == offset_axis else 0
+            idx.append(slice(start, start + shape[ax]))
+        a = t[tuple(idx)].cpu().numpy()
+        return np.ascontiguousarray(np.transpose(a, (0,) + tuple(range(self.dim, 0, -1))))
+
+    def centered_from_numpy(self, a) -> torch.Tensor:
+        return self._to_dev(a, self.cext)
+
+    def centered_to_numpy(self, t, squeeze=True) -> np.ndarray:
+        a = self._to_host(t, self.res)
+        return a[0] if (squeeze and self.batch == 1) else a
+
+    def face_shapes(self, vspec):
+        shapes, offsets = [], []
+        for c in range(self.dim):
+            lo, hi = stored_faces(vspec, c)
+            s = list(self.res); s[c] = self.res[c] - 1 + int(lo) + int(hi)
+            shapes.append(tuple(s)); offsets.append(0 if lo else 1)
+        return shapes, offsets
+
+    def faces_from_numpy(self, comps, vspec) -> List[torch.Tensor]:
+        shapes, offsets = self.face_shapes(vspec)
+        out = []
+        for c in range(self.dim):
+            a = np.asarray(comps[c], dtype=np.float32)
+            assert tuple(a.shape[-self.dim:]) == shapes[c], f"component {c}: shape {a.shape} != stored faces {shapes[c]}"
+            out.append(self._to_dev(a, self.fext, c, offsets[c]))
+        return out
+
+    def faces_to_numpy(self, ts, vspec, squeeze=True):
+        shapes, offsets = self.face_shapes(vspec)
+        out = []
+        for c in range(self.dim):
+            a = self._to_host(ts[c], shapes[c], c, offsets[c])
+            out.append(a[0] if (squeeze and self.batch == 1) else a)
+        return out
+
+
+# ---- one function per exported entry point ---------------------------------------------------------------------------------
+
+def laplace(dom: Domain, bc, x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+    """field.laplace order 2 (phi/field/_field_math.py:118-145)."""
+    require_cuda()
+    out = dom.alloc_centered() if out is None else out
+    _lib.check(_lib.load().phicuda_laplace_f32(C.byref(dom.grid), C.byref(make_bc(bc)), _ptr(x), _ptr(out), _stream()))
+    return out
+
+
+def laplace_axpy(dom: Domain, bc, x, coeff: float, out=None):
+    """x + coeff * laplace(x): one explicit diffusion sub-step (phi/physics/diffuse.py:13-60)."""
+    require_cuda()
+    out = dom.alloc_centered() if out is None else out
+    _lib.check(_lib.load().phicuda_laplace_axpy_f32(C.byref(dom.grid), C.byref(make_bc(bc)), _ptr(x), C.c_float(coeff), _ptr(out), _stream()))
+    return out
+
+
+def divergence(dom: Domain, vbc, v: List[torch.Tensor], out=None):
+    """field.divergence of a staggered grid (phi/field/_field_math.py:617-626)."""
+    require_cuda()
+    out = dom.alloc_centered() if out is None else out
+    _lib.check(_lib.load().phicuda_divergence_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(v), _ptr(out), _stream()))
+    return out
+
+
+def grad_sub(dom: Domain, vbc, v: List[torch.Tensor], p: torch.Tensor):
+    """v -= spatial_gradient(p, at='face') in place (phi/physics/fluid.py:158-161)."""
+    require_cuda()
+    _lib.check(_lib.load().phicuda_grad_sub_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(v), _ptr(p), _stream()))
+    return v
+
+
+def advect_centered(dom: Domain, vbc, vel, fbc, src, dt: float, out=None):
+    """advect.semi_lagrangian of a centred field (phi/physics/advect.py:156-179)."""
+    require_cuda()
+    out = dom.alloc_centered() if out is None else out
+    _lib.check(_lib.load().phicuda_advect_centered_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(vel),
+                                                       C.byref(make_bc(fbc)), _ptr(src), _ptr(out), C.c_float(dt), _stream()))
+    return out
+
+
+def advect_staggered(dom: Domain, vbc, vel, fbc, src, dt: float, out=None):
+    """advect.semi_lagrangian of a staggered field (self-advection when src is vel)."""
+    require_cuda()
+    out = dom.alloc_faces() if out is None else out
+    _lib.check(_lib.load().phicuda_advect_staggered_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(vel),
+                                                        C.byref(make_vbc(fbc, dom.dim)), _f3(src), _f3(out), C.c_float(dt), _stream()))
+    return out
+
+
+def mac_cormack_centered(dom: Domain, vbc, vel, fbc, src, dt: float, correction_strength=1.0, out=None):
+    """advect.mac_cormack of a centred field (phi/physics/advect.py:182-215)."""
+    require_cuda()
+    out = dom.alloc_centered() if out is None else out
+    tmp = dom.alloc_centered()
+    _lib.check(_lib.load().phicuda_mac_cormack_centered_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(vel),
+                                                            C.byref(make_bc(fbc)), _ptr(src), _ptr(out), _ptr(tmp),
+                                                            C.c_float(dt), C.c_float(correction_strength), _stream()))
+    return out
+
+
+def axpy_centered(dom: Domain, a: float, x, y):
+    require_cuda()
+    _lib.check(_lib.load().phicuda_axpy_centered_f32(C.byref(dom.grid), C.c_float(a), _ptr(x), _ptr(y), _stream()))
+    return y
+
+
+def add_buoyancy(dom: Domain, vbc, sbc, s, factor: Sequence[float], dt: float, v):
+    """v += dt * resample(s * factor, to=v) in place (phi/field/_resample.py:272-276)."""
+    require_cuda()
+    b = (C.c_float * 3)(*[float(factor[i]) if i < len(factor) else 0.0 for i in range(3)])
+    _lib.check(_lib.load().phicuda_add_buoyancy_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), C.byref(make_bc(sbc)),
+                                                    _ptr(s), b, C.c_float(dt), _f3(v), _stream()))
+    return v
+
+
+def _is_flexible(vspec) -> bool:
+    spec = vspec[0] if isinstance(vspec, list) else vspec
+    return any(side == ZG for ax in spec for side in ax)
+
+
+def cg_params(vbc, rtol=1e-5, atol=1e-5, max_iter=1000, matrix_offset=0.0, balance=None) -> PhiCgParams:
+    """Solver parameters with the defaults of fluid.make_incompressible (phi/physics/fluid.py:145-148):
+    non-flexible velocity boundaries (closed / periodic) -> balanced right-hand side and rank deficiency 1."""
+    rank_def = not _is_flexible(vbc)
+    prm = PhiCgParams()
+    prm.rtol, prm.atol, prm.max_iter = rtol, atol, int(max_iter)
+    prm.balance_rhs = int(rank_def if balance is None else balance)
+    prm.project_mean = int(rank_def)
+    prm.matrix_offset = float(matrix_offset) if rank_def else 0.0
+    return prm
+
+
+def read_results(dom: Domain) -> np.ndarray:
+    """Synchronises and returns the per-batch solve results as a structured array."""
+    _, res = dom.workspace()
+    return res.cpu().numpy().view(_RESULT_DTYPE)
+
+
+def cg_poisson(dom: Domain, vbc, rhs, x0=None, prm: PhiCgParams = None):
+    """Pressure solve: CG on the matrix-free Poisson operator (phi/physics/fluid.py:156). Returns x (x0 updated in place)."""
+    require_cuda()
+    ws, res = dom.workspace()
+    x = dom.alloc_centered() if x0 is None else x0
+    prm = prm or cg_params(vbc)
+    _lib.check(_lib.load().phicuda_cg_poisson_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _ptr(rhs), _ptr(x), C.byref(prm),
+                                                  _ptr(res), _ptr(ws), C.c_size_t(ws.numel()), _stream()))
+    return x
+
+
+def make_incompressible(dom: Domain, vbc, v, p=None, prm: PhiCgParams = None):
+    """fluid.make_incompressible on raw arrays: v and p are updated in place."""
+    require_cuda()
+    ws, res = dom.workspace()
+    p = dom.alloc_centered() if p is None else p
+    div = dom.alloc_centered()
+    prm = prm or cg_params(vbc)
+    _lib.check(_lib.load().phicuda_make_incompressible_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(v), _ptr(p), _ptr(div),
+                                                           C.byref(prm), _ptr(res), _ptr(ws), C.c_size_t(ws.numel()), _stream()))
+    return v, p
+
+
+def plume_step(dom: Domain, vbc, sbc, v, s, p, inflow, dt, inflow_rate, buoyancy, prm: PhiCgParams, mac_cormack=False):
+    """incompressible_step: the fused notebook step (examples/grids/Smoke_Plume.ipynb:58-68); state updated in place."""
+    require_cuda()
+    ws, res = dom.workspace()
+    sp = PhiPlumeParams()
+    sp.dt, sp.inflow_rate, sp.mac_cormack = dt, inflow_rate, int(mac_cormack)
+    for i in range(3):
+        sp.buoyancy[i] = float(buoyancy[i]) if i < len(buoyancy) else 0.0
+    _lib.check(_lib.load().phicuda_plume_step_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), C.byref(make_bc(sbc)), _f3(v),
+                                                  _ptr(s), _ptr(p), _ptr(inflow), C.byref(sp), C.byref(prm), _ptr(res),
+                                                  _ptr(dom.scratch()), _ptr(ws), C.c_size_t(ws.numel()), _stream()))
+    return v, s, p

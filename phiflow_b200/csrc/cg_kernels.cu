@@ -1,0 +1,424 @@
+// A2 + A12: conjugate gradients on the matrix-free pressure Poisson operator  --  ONE persistent cooperative kernel
+// per solve.
+//
+// Reference algorithm: Shewchuk CG as written in PhiML/phiml/backend/_linalg.py:52-90 with the stopping rule of
+// stop_on_l2 (:23-40) and the rank-1 offset of linear() (:784-789), applied by the reference to an explicit CSR matrix
+// that it obtains by tracing fluid.masked_laplace (phi/physics/fluid.py:165-202).  Here the operator is applied on the
+// fly (it is the 5/7-point laplace with the PRESSURE boundary), and the iteration is reorganised
+// into two grid-wide passes with 32 B/cell of HBM traffic instead of the textbook three passes / 44 B:
+//
+//   pass A:  d' = r + beta*d          (written)          dq = sum d' * (A d')       S = sum d'
+//            -- grid barrier --       alpha = delta / (dq + c*S^2)
+//   pass B:  q = A d' + c*S  (recomputed, never stored)  x += alpha*d'   r -= alpha*q    delta' = sum r*r
+//            -- grid barrier --       beta = delta'/delta, convergence test per batch entry
+//
+// d is double-buffered because pass A needs the OLD d in the halo cells of neighbouring tiles.  Dot products are
+// accumulated per thread in fp32 over at most a few hundred cells, then in fp64 across warps / CTAs in a fixed order
+// (deterministic, independent of scheduling).  Every CTA redundantly reduces the per-CTA partials and therefore
+// takes identical control-flow decisions; nothing returns to the host until the solve is over.
+#include <cooperative_groups.h>
+#include "phi_internal.cuh"
+#include "launch.cuh"
+
+namespace cg = cooperative_groups;
+
+#define CG_MAX_BATCH 1024
+
+struct CgArgs {
+    DGrid g; DField pf; UnitMap um;
+    const float* rhs; float* x; float* r; float* d0; float* d1;
+    double* partials;              // [2 regions][2 accumulators][batch][grid]
+    PhiCgResult* result;
+    PhiCgParams prm;
+};
+
+struct CgShared {                   // per-thread view of the CTA's shared memory (pointers carved from one dynamic block)
+    double (*warp_acc)[PHI_WARPS_PER_CTA];   // [2][warps]
+    double* sum0;                  // reduced accumulator 0 per batch entry
+    double* sum1;
+    double* delta;
+    float* alpha;
+    float* beta;
+    float* offs;                   // c * S  (offset part of q)
+    float* mean;
+    float* tol_sq;
+    float* rsq0;
+    int* iters;
+    int* any_cont;
+    unsigned char *cont, *conv, *divg;
+};
+
+__host__ __device__ inline size_t cg_smem_bytes(int batch)
+{
+    const size_t b8 = ((size_t)batch + 1) / 2 * 2;      // keep 8-byte alignment of what follows
+    return 2 * PHI_WARPS_PER_CTA * sizeof(double) + 3 * b8 * sizeof(double) + 6 * b8 * sizeof(float)
+         + (b8 + 2) * sizeof(int) + 3 * (b8 + 16);
+}
+
+__device__ __forceinline__ CgShared cg_carve(unsigned char* base, int batch)
+{
+    const size_t b8 = ((size_t)batch + 1) / 2 * 2;
+    CgShared sh;
+    unsigned char* p = base;
+    sh.warp_acc = reinterpret_cast<double (*)[PHI_WARPS_PER_CTA]>(p); p += 2 * PHI_WARPS_PER_CTA * sizeof(double);
+    sh.sum0 = (double*)p; p += b8 * sizeof(double);
+    sh.sum1 = (double*)p; p += b8 * sizeof(double);
+    sh.delta = (double*)p; p += b8 * sizeof(double);
+    sh.alpha = (float*)p; p += b8 * sizeof(float);
+    sh.beta = (float*)p; p += b8 * sizeof(float);
+    sh.offs = (float*)p; p += b8 * sizeof(float);
+    sh.mean = (float*)p; p += b8 * sizeof(float);
+    sh.tol_sq = (float*)p; p += b8 * sizeof(float);
+    sh.rsq0 = (float*)p; p += b8 * sizeof(float);
+    sh.iters = (int*)p; p += b8 * sizeof(int);
+    sh.any_cont = (int*)p; p += 2 * sizeof(int);
+    sh.cont = p; p += b8 + 16;
+    sh.conv = p; p += b8;
+    sh.divg = p;
+    return sh;
+}
+
+// ---- sources / epilogues ---------------------------------------------------------------------------------
+
+struct SrcDirection {          // d' = r + beta*d
+    const float* r; const float* d; float beta;
+    __device__ __forceinline__ float4 load4(long long off) const
+    {
+        float4 a = *reinterpret_cast<const float4*>(r + off);
+        if (beta != 0.f) {
+            const float4 o = *reinterpret_cast<const float4*>(d + off);
+            a.x += beta * o.x; a.y += beta * o.y; a.z += beta * o.z; a.w += beta * o.w;
+        }
+        return a;
+    }
+    __device__ __forceinline__ float load1(long long off) const
+    {
+        float a = r[off];
+        if (beta != 0.f) a += beta * d[off];
+        return a;
+    }
+};
+
+struct EpiResidual0 {          // r = (rhs - mean) - A x0 [- c*sum(x0)];  acc0 = |r|^2, acc1 = |r without offset|^2
+    const float* rhs; float* r; float mean; float offs;
+    float acc0, acc1;
+    __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid)
+    {
+        const float4 y = *reinterpret_cast<const float4*>(rhs + off);
+        float4 rt;                                    // residual without offset (tolerance reference, _linalg.py:61-67)
+        rt.x = (y.x - mean) - q.x; rt.y = (y.y - mean) - q.y; rt.z = (y.z - mean) - q.z; rt.w = (y.w - mean) - q.w;
+        float4 rr = make_float4(rt.x - offs, rt.y - offs, rt.z - offs, rt.w - offs);
+        if (nvalid == 4) {
+            *reinterpret_cast<float4*>(r + off) = rr;
+            acc0 += rr.x * rr.x + rr.y * rr.y + rr.z * rr.z + rr.w * rr.w;
+            acc1 += rt.x * rt.x + rt.y * rt.y + rt.z * rt.z + rt.w * rt.w;
+        } else {
+            for (int j = 0; j < nvalid; ++j) {
+                const float a = f4_get(rr, j), t = f4_get(rt, j);
+                r[off + j] = a; acc0 += a * a; acc1 += t * t;
+            }
+        }
+    }
+};
+
+struct EpiPassA {              // store d', acc0 = d'.(A d'), acc1 = sum d'
+    float* dnew; float acc0, acc1;
+    __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid)
+    {
+        if (nvalid == 4) {
+            *reinterpret_cast<float4*>(dnew + off) = c;
+            acc0 += c.x * q.x + c.y * q.y + c.z * q.z + c.w * q.w;
+            acc1 += (c.x + c.y) + (c.z + c.w);
+        } else {
+            for (int j = 0; j < nvalid; ++j) { const float v = f4_get(c, j); dnew[off + j] = v; acc0 += v * f4_get(q, j); acc1 += v; }
+        }
+    }
+};
+
+struct EpiPassB {              // x += alpha d', r -= alpha (A d' + c S), acc0 = |r|^2
+    float* x; float* r; float alpha; float offs; float acc0, acc1;
+    __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid)
+    {
+        if (nvalid == 4) {
+            float4 xv = *reinterpret_cast<float4*>(x + off);
+            float4 rv = *reinterpret_cast<float4*>(r + off);
+            xv.x += alpha * c.x; xv.y += alpha * c.y; xv.z += alpha * c.z; xv.w += alpha * c.w;
+            rv.x -= alpha * (q.x + offs); rv.y -= alpha * (q.y + offs); rv.z -= alpha * (q.z + offs); rv.w -= alpha * (q.w + offs);
+            *reinterpret_cast<float4*>(x + off) = xv;
+            *reinterpret_cast<float4*>(r + off) = rv;
+            acc0 += rv.x * rv.x + rv.y * rv.y + rv.z * rv.z + rv.w * rv.w;
+        } else {
+            for (int j = 0; j < nvalid; ++j) {
+                const float xv = x[off + j] + alpha * f4_get(c, j);
+                const float rv = r[off + j] - alpha * (f4_get(q, j) + offs);
+                x[off + j] = xv; r[off + j] = rv; acc0 += rv * rv;
+            }
+        }
+    }
+};
+
+// ---- helpers ------------------------------------------------------------------------------------------------
+
+// Iterate over the cells of a warp unit without a stencil (sums, final mean removal).
+template <int DIM, class F>
+__device__ __forceinline__ void for_unit_cells(const DGrid& g, const DField& pf, const WarpUnit& w, F&& fn)
+{
+    const int lane = threadIdx.x & 31;
+    const int x0 = w.xt0 + lane * 4;
+    if (x0 >= g.n[0]) return;
+    const int nvalid = min(4, g.n[0] - x0);
+    for (int m = w.m0; m < w.m1; ++m) {
+        const long long off = (long long)w.b * pf.sb + (DIM == 3 ? (long long)m * pf.sz + (long long)w.t * pf.sy : (long long)m * pf.sy) + x0;
+        fn(off, nvalid);
+    }
+}
+
+// Block-level flush of the two fp32 thread accumulators of the current batch entry into partials[region][k][b][cta].
+__device__ __forceinline__ void flush_partials(const CgShared& sh, double* partials, int region, int batch, int b, double a0, double a1)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    a0 = warp_sum(a0); a1 = warp_sum(a1);
+    if (lane == 0) { sh.warp_acc[0][warp] = a0; sh.warp_acc[1][warp] = a1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s0 = 0, s1 = 0;
+        for (int w = 0; w < PHI_WARPS_PER_CTA; ++w) { s0 += sh.warp_acc[0][w]; s1 += sh.warp_acc[1][w]; }
+        const size_t G = gridDim.x;
+        partials[((size_t)(region * 2 + 0) * batch + b) * G + blockIdx.x] = s0;
+        partials[((size_t)(region * 2 + 1) * batch + b) * G + blockIdx.x] = s1;
+    }
+    __syncthreads();
+}
+
+// After a grid barrier: every CTA sums, in a fixed order, the partials of the CTAs that own units of batch entry b.
+__device__ __forceinline__ void reduce_partials(const CgShared& sh, const double* partials, int region, int batch, int units_per_batch,
+                                                const unsigned char* active)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = gridDim.x;
+    const int cnt = min(units_per_batch, G);
+    for (int b = warp; b < batch; b += PHI_WARPS_PER_CTA) {
+        if (active && !active[b]) continue;
+        const int first = (int)(((long long)b * units_per_batch) % G);
+        double s0 = 0, s1 = 0;
+        for (int i = lane; i < cnt; i += 32) {
+            int c = first + i; if (c >= G) c -= G;
+            s0 += __ldcg(&partials[((size_t)(region * 2 + 0) * batch + b) * G + c]);
+            s1 += __ldcg(&partials[((size_t)(region * 2 + 1) * batch + b) * G + c]);
+        }
+        s0 = warp_sum(s0); s1 = warp_sum(s1);
+        if (lane == 0) { sh.sum0[b] = s0; sh.sum1[b] = s1; }
+    }
+    __syncthreads();
+}
+
+// ---- the solver ---------------------------------------------------------------------------------------------
+
+template <int DIM>
+__global__ void __launch_bounds__(PHI_WARPS_PER_CTA * 32, 2)
+k_cg_poisson(CgArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CgShared sh = cg_carve(smem_raw, a.g.batch);
+    cg::grid_group grid = cg::this_grid();
+    const DGrid& g = a.g;
+    const UnitMap& um = a.um;
+    const int warp = threadIdx.x >> 5;
+    const int batch = g.batch;
+    const double cells = (double)g.n[0] * g.n[1] * g.n[2];
+    const float coffs = a.prm.matrix_offset;
+    int region = 0;
+
+    // Runs `body(w, acc0, acc1)` over the units of this CTA, flushing the accumulators whenever the batch entry changes.
+    auto sweep = [&](const unsigned char* active, auto&& body) {
+        int cur_b = -1; float acc0 = 0.f, acc1 = 0.f;
+        for (int unit = blockIdx.x; unit < um.total_units; unit += gridDim.x) {
+            const int b = unit / um.units_per_batch;
+            if (active && !active[b]) continue;
+            if (b != cur_b) {
+                if (cur_b >= 0) flush_partials(sh, a.partials, region, batch, cur_b, acc0, acc1);
+                cur_b = b; acc0 = 0.f; acc1 = 0.f;
+            }
+            const WarpUnit w = phi_warp_unit<DIM>(g, um, unit, warp);
+            if (w.valid) body(w, acc0, acc1);
+        }
+        if (cur_b >= 0) flush_partials(sh, a.partials, region, batch, cur_b, acc0, acc1);
+    };
+    auto barrier_and_reduce = [&](const unsigned char* active) {
+        grid.sync();
+        reduce_partials(sh, a.partials, region, batch, um.units_per_batch, active);
+        region ^= 1;
+    };
+
+    for (int b = threadIdx.x; b < batch; b += blockDim.x) { sh.mean[b] = 0.f; sh.offs[b] = 0.f; }
+    __syncthreads();
+
+    // ---- setup: mean(rhs) for the balanced right-hand side, sum(x0) for the offset term -----------------------
+    if (a.prm.balance_rhs || coffs != 0.f) {
+        sweep(nullptr, [&](const WarpUnit& w, float& acc0, float& acc1) {
+            for_unit_cells<DIM>(g, a.pf, w, [&](long long off, int nvalid) {
+                for (int j = 0; j < nvalid; ++j) { acc0 += a.rhs[off + j]; acc1 += a.x[off + j]; }
+            });
+        });
+        barrier_and_reduce(nullptr);
+        for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+            sh.mean[b] = a.prm.balance_rhs ? (float)(sh.sum0[b] / cells) : 0.f;
+            sh.offs[b] = coffs * (float)sh.sum1[b];
+        }
+        __syncthreads();
+    }
+
+    // ---- r0 = y - (A + c 11^T) x0,  delta0 -----------------------------------------------------------------------
+    sweep(nullptr, [&](const WarpUnit& w, float& acc0, float& acc1) {
+        SrcArray src{a.x};
+        EpiResidual0 epi{a.rhs, a.r, sh.mean[w.b], sh.offs[w.b], 0.f, 0.f};
+        phi_march<DIM>(g, a.pf, src, epi, w.b, w.xt0, w.t, w.m0, w.m1);
+        acc0 += epi.acc0; acc1 += epi.acc1;
+    });
+    barrier_and_reduce(nullptr);
+    for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+        const double d0 = sh.sum0[b], d0tol = sh.sum1[b];
+        sh.delta[b] = d0;
+        const float tol = fmaxf(a.prm.rtol * a.prm.rtol * (float)d0tol, a.prm.atol * a.prm.atol);
+        sh.tol_sq[b] = tol; sh.rsq0[b] = (float)d0;
+        const bool conv = (float)d0 <= tol;
+        const bool divg = !isfinite((float)d0);
+        sh.conv[b] = conv; sh.divg[b] = divg; sh.iters[b] = 0;
+        sh.cont[b] = (!conv && !divg && a.prm.max_iter > 0) ? 1 : 0;
+        sh.beta[b] = 0.f; sh.alpha[b] = 0.f;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { int any = 0; for (int b = 0; b < batch; ++b) any |= sh.cont[b]; *sh.any_cont = any; }
+    __syncthreads();
+
+    float* dold = a.d0; float* dnew = a.d1;
+    while (*sh.any_cont) {
+        // ---- pass A ---------------------------------------------------------------------------------------------
+        sweep(sh.cont, [&](const WarpUnit& w, float& acc0, float& acc1) {
+            SrcDirection src{a.r, dold, sh.beta[w.b]};
+            EpiPassA epi{dnew, 0.f, 0.f};
+            phi_march<DIM>(g, a.pf, src, epi, w.b, w.xt0, w.t, w.m0, w.m1);
+            acc0 += epi.acc0; acc1 += epi.acc1;
+        });
+        barrier_and_reduce(sh.cont);
+        for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+            if (!sh.cont[b]) continue;
+            const double S = sh.sum1[b];
+            const double dq = sh.sum0[b] + (double)coffs * S * S;
+            sh.alpha[b] = (dq != 0.0) ? (float)(sh.delta[b] / dq) : 0.f;      // divide_no_nan (_linalg.py:74)
+            sh.offs[b] = coffs * (float)S;
+        }
+        __syncthreads();
+        // ---- pass B ---------------------------------------------------------------------------------------------
+        sweep(sh.cont, [&](const WarpUnit& w, float& acc0, float& acc1) {
+            SrcArray src{dnew};
+            EpiPassB epi{a.x, a.r, sh.alpha[w.b], sh.offs[w.b], 0.f, 0.f};
+            phi_march<DIM>(g, a.pf, src, epi, w.b, w.xt0, w.t, w.m0, w.m1);
+            acc0 += epi.acc0;
+        });
+        barrier_and_reduce(sh.cont);
+        for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+            if (!sh.cont[b]) continue;
+            const double dn = sh.sum0[b];
+            const double dold_ = sh.delta[b];
+            sh.beta[b] = (dold_ != 0.0) ? (float)(dn / dold_) : 0.f;
+            sh.delta[b] = dn;
+            const int it = ++sh.iters[b];
+            const float rsq = fabsf((float)dn);
+            const bool conv = rsq <= sh.tol_sq[b];
+            bool divg = !isfinite(rsq) || (rsq / sh.rsq0[b] > 1e5f && it >= 8);   // stop_on_l2 (_linalg.py:29-36)
+            sh.conv[b] = conv; sh.divg[b] = divg;
+            sh.cont[b] = (!conv && !divg && it < a.prm.max_iter) ? 1 : 0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { int any = 0; for (int b = 0; b < batch; ++b) any |= sh.cont[b]; *sh.any_cont = any; }
+        __syncthreads();
+        float* t = dold; dold = dnew; dnew = t;
+    }
+
+    // ---- zero-mean solution of the rank-deficient system ------------------------------------------------------
+    if (a.prm.project_mean) {
+        sweep(nullptr, [&](const WarpUnit& w, float& acc0, float& acc1) {
+            for_unit_cells<DIM>(g, a.pf, w, [&](long long off, int nvalid) {
+                for (int j = 0; j < nvalid; ++j) acc0 += a.x[off + j];
+            });
+        });
+        barrier_and_reduce(nullptr);
+        for (int unit = blockIdx.x; unit < um.total_units; unit += gridDim.x) {
+            const WarpUnit w = phi_warp_unit<DIM>(g, um, unit, warp);
+            if (!w.valid) continue;
+            const float m = (float)(sh.sum0[w.b] / cells);
+            for_unit_cells<DIM>(g, a.pf, w, [&](long long off, int nvalid) {
+                for (int j = 0; j < nvalid; ++j) a.x[off + j] -= m;
+            });
+        }
+    }
+
+    if (blockIdx.x == 0) {
+        for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+            PhiCgResult res;
+            res.iterations = sh.iters[b]; res.converged = sh.conv[b]; res.diverged = sh.divg[b];
+            res.residual_sq = fabsf((float)sh.delta[b]); res.tol_sq = sh.tol_sq[b]; res.initial_residual_sq = sh.rsq0[b];
+            a.result[b] = res;
+        }
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------
+
+static int cg_grid_size(int dim, int batch, int* blocks_per_sm_out)
+{
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t smem = cg_smem_bytes(batch);
+    if (dim == 3) {
+        cudaFuncSetAttribute(k_cg_poisson<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_poisson<3>, PHI_WARPS_PER_CTA * 32, smem);
+    } else {
+        cudaFuncSetAttribute(k_cg_poisson<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_poisson<2>, PHI_WARPS_PER_CTA * 32, smem);
+    }
+    if (blocks_per_sm_out) *blocks_per_sm_out = per_sm;
+    return sms * per_sm;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// workspace layout: r | d0 | d1 | partials[2][2][batch][max_grid]
+#define CG_MAX_GRID 2048
+size_t phi_cg_workspace_bytes(const DGrid& g)
+{
+    const size_t pf_sb = (size_t)g.cext[0] * g.cext[1] * g.cext[2];
+    const size_t arr = align_up((size_t)pf_sb * g.batch * sizeof(float), 256);
+    return 3 * arr + align_up((size_t)4 * g.batch * CG_MAX_GRID * sizeof(double), 256);
+}
+
+int phi_launch_cg(const CgLaunch& l, cudaStream_t s)
+{
+    const DGrid& g = l.g;
+    if (g.batch > CG_MAX_BATCH) { phi_set_error("cg: batch %d exceeds %d (split the batch)", g.batch, CG_MAX_BATCH); return PHI_ERR_UNSUPPORTED; }
+    if (l.workspace_bytes < phi_cg_workspace_bytes(g)) { phi_set_error("cg: workspace %zu < %zu bytes", l.workspace_bytes, phi_cg_workspace_bytes(g)); return PHI_ERR_WORKSPACE; }
+    int per_sm = 0;
+    int grid = cg_grid_size(g.dim, g.batch, &per_sm);
+    if (grid <= 0) { phi_set_error("cg: kernel does not fit on the device (occupancy 0)"); return PHI_ERR_INVALID; }
+    const size_t pf_sb = (size_t)g.cext[0] * g.cext[1] * g.cext[2];
+    CgArgs a;
+    a.g = g; a.pf = l.pf;
+    a.um = phi_make_unit_map(g, grid * 8);
+    if (grid > a.um.total_units) grid = a.um.total_units;
+    if (grid > CG_MAX_GRID) grid = CG_MAX_GRID;
+    const size_t arr = align_up((size_t)pf_sb * g.batch * sizeof(float), 256);
+    unsigned char* ws = (unsigned char*)l.workspace;
+    a.rhs = l.rhs; a.x = l.x;
+    a.r = (float*)ws; a.d0 = (float*)(ws + arr); a.d1 = (float*)(ws + 2 * arr);
+    a.partials = (double*)(ws + 3 * arr);
+    a.result = l.result; a.prm = l.prm;
+    void* args[] = {&a};
+    const size_t smem = cg_smem_bytes(g.batch);
+    cudaError_t err;
+    if (g.dim == 3) err = cudaLaunchCooperativeKernel((void*)k_cg_poisson<3>, dim3(grid), dim3(PHI_WARPS_PER_CTA * 32), args, smem, s);
+    else            err = cudaLaunchCooperativeKernel((void*)k_cg_poisson<2>, dim3(grid), dim3(PHI_WARPS_PER_CTA * 32), args, smem, s);
+    if (err != cudaSuccess) { phi_set_error("cg: cooperative launch failed: %s", cudaGetErrorString(err)); return (int)err; }
+    return 0;
+}

@@ -1,0 +1,25 @@
+// Host-side launchers implemented in the kernel translation units, called from api.cu.
+#pragma once
+#include "phi_internal.cuh"
+
+int phi_launch_laplace(const DGrid& g, const DField& f, const float* x, float* y, float coeff, bool axpy, cudaStream_t s);
+int phi_launch_divergence(const DGrid& g, const DVec& v, const DField& cf, float* div, cudaStream_t s);
+int phi_launch_grad_sub(const DGrid& g, const DVec& vin, const DVecOut& v, const DField& pf, const float* p, cudaStream_t s);
+int phi_launch_buoyancy(const DGrid& g, const DVec& vin, const DVecOut& v, const DField& sf, const float* sarr,
+                        const float b[3], float dt, cudaStream_t s);
+int phi_launch_axpy(const DGrid& g, const DField& cf, float a, const float* x, float* y, cudaStream_t s);
+
+// target_comp < 0: centred field
+int phi_launch_advect(const DGrid& g, const DVec& vel, const DField& ff, int target_comp, const float* src, float* dst,
+                      float dt, cudaStream_t s);
+int phi_launch_mac_cormack(const DGrid& g, const DVec& vel, const DField& ff, const float* src, float* dst, float* tmp,
+                           float dt, float strength, cudaStream_t s);
+
+struct CgLaunch {
+    DGrid g; DField pf;
+    const float* rhs; float* x;
+    PhiCgParams prm; PhiCgResult* result;
+    void* workspace; size_t workspace_bytes;
+};
+size_t phi_cg_workspace_bytes(const DGrid& g);
+int phi_launch_cg(const CgLaunch& a, cudaStream_t s);
