@@ -1,6 +1,7 @@
 // C ABI of libphicuda.so (declared in include/phicuda.h): argument validation, descriptor construction, launch order.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "phi_internal.cuh"
 #include "launch.cuh"
@@ -13,6 +14,12 @@ void phi_set_error(const char* fmt, ...)
     va_list ap; va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+bool phi_ring_enabled()
+{
+    const char* v = getenv("PHICUDA_NO_RING");       // diagnostics: force the register-marching kernels
+    return !(v && v[0] == '1');
 }
 
 static int cuda_fail(int err, const char* what)

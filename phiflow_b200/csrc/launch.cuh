@@ -22,4 +22,8 @@ struct CgLaunch {
     void* workspace; size_t workspace_bytes;
 };
 size_t phi_cg_workspace_bytes(const DGrid& g);
+// TMA ring fast paths (ring_kernels.cu); return -100 when the shape does not fit and the caller must fall back
+int phi_launch_laplace_ring(const DGrid& g, const DField& f, const float* x, float* y, float coeff, bool axpy, cudaStream_t s);
+int phi_launch_cg_ring(const CgLaunch& a, cudaStream_t s);
+bool phi_ring_enabled();
 int phi_launch_cg(const CgLaunch& a, cudaStream_t s);

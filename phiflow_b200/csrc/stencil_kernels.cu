@@ -34,6 +34,10 @@ k_laplace(DGrid g, DField f, UnitMap um, const float* __restrict__ x, float* __r
 
 int phi_launch_laplace(const DGrid& g, const DField& f, const float* x, float* y, float coeff, bool axpy, cudaStream_t s)
 {
+    if (phi_ring_enabled()) {
+        const int e = phi_launch_laplace_ring(g, f, x, y, coeff, axpy, s);
+        if (e != -100) return e;
+    }
     UnitMap um = phi_make_unit_map(g, 148 * 16);
     const int blocks = um.total_units;
     dim3 block(PHI_WARPS_PER_CTA * 32);
