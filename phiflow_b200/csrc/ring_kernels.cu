@@ -11,6 +11,10 @@
 // and halo planes are fetched from wherever the boundary condition says the ghost values live:
 //   PERIODIC -> the wrapped line, ZERO_GRADIENT -> the clamped line, constant -> not fetched (consumers substitute c).
 // x ghosts are read from the staged line itself.  Outputs go straight from registers to global memory (STG.128).
+//
+// The consumer loop is issue-bound if written naively (first ncu capture: 200+ instructions per 4 cells), so every
+// thread precomputes the geometry of the <= 4 float4 groups it owns once per kernel, boundary flags once per tile, and
+// the common case runs a branch-free path: 5 LDS.128 + 2 SHFL + ~40 FP32 ops + 1 STG.128 per group.
 #include <cooperative_groups.h>
 #include "cg_common.cuh"
 #include "launch.cuh"
@@ -20,12 +24,15 @@ namespace cg = cooperative_groups;
 #define RING_CONSUMERS 256
 #define RING_THREADS (RING_CONSUMERS + 32)
 #define RING_MAX_STAGES 8
+#define RING_G 4                 // float4 groups per consumer thread and plane (TY * nx4 <= RING_G * 256)
 
 struct RingCfg {
     int TY, R, pitch, nx4;
     int stage_floats;          // floats between consecutive stages
     int ZC, nyt, nzc;
     int units_per_batch, total_units;
+    int groups;                // ceil(TY * nx4 / 256)
+    int shfl_ok;               // lanes of a warp own consecutive groups of one line -> x neighbours via shuffles
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
@@ -56,21 +63,26 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // ---- ring state (per thread, registers) ------------------------------------------------------------------------------
+struct SlotIt {                 // a position in the ring: slot index + parity of its current use
+    int slot; unsigned par;
+    __device__ __forceinline__ void next(int R) { if (++slot == R) { slot = 0; par ^= 1u; } }
+};
+
 struct Ring {
     float* stage0;
     uint32_t stage0_s, full0, empty0;
-    unsigned idx;              // planes produced (producer) / fully processed base index (consumers)
+    SlotIt pos;                // next plane to produce (producer) / first plane of the next unit (consumers)
 };
 
 __device__ __forceinline__ void ring_init(Ring& rg, unsigned char* smem, const RingCfg& cfg)
 {
-    // layout: [R full barriers][R empty barriers][pad to 128][stages]
+    // layout: [8 full barriers][8 empty barriers][stages]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     rg.full0 = smem_u32(bars);
     rg.empty0 = smem_u32(bars + RING_MAX_STAGES);
     rg.stage0 = reinterpret_cast<float*>(smem + 128);
     rg.stage0_s = smem_u32(rg.stage0);
-    rg.idx = 0;
+    rg.pos.slot = 0; rg.pos.par = 0;
     if (threadIdx.x == 0) {
         for (int s = 0; s < cfg.R; ++s) {
             mbar_init(rg.full0 + 8 * s, 1);
@@ -81,114 +93,220 @@ __device__ __forceinline__ void ring_init(Ring& rg, unsigned char* smem, const R
     __syncthreads();
 }
 
-// Producer warp: stage the lines of one plane.  hsrc: NH haloed arrays (TY+2 lines), esrc: NE element-wise arrays (TY lines).
+// Producer warp.  Lane l owns staged lines l, l+32, l+64, l+96 of a stage: first the NH haloed arrays (TY+2 lines
+// each), then the NE element-wise arrays (TY lines each).  Everything that does not depend on the plane is resolved once
+// per unit (ProdUnit); per plane the producer only resolves z, adds it to the line offsets and issues the bulk copies -
+// the producer is a single warp, so its serial instruction count per plane bounds the whole pipeline.
+struct ProdUnit {
+    long long yoff[4];          // b*sb + y*sy of the source line (boundary already applied to y)
+    const float* base[4];       // source array
+    uint32_t dsto[4];           // byte offset of the destination line inside a stage
+    unsigned hmask, emask;      // which of the 4 lines are active haloed / element-wise lines
+    int tot_h, tot_e;           // warp totals of active lines
+};
+
 template <int DIM>
-__device__ __forceinline__ void ring_produce(Ring& rg, const RingCfg& cfg, const DGrid& g, const DField& pf,
-                                             int NH, int NE, const float* const* hsrc, const float* const* esrc,
-                                             int b, int y0, int z, bool interior)
+__device__ __forceinline__ void prod_unit_setup(ProdUnit& pu, const RingCfg& cfg, const DGrid& g, const DField& pf,
+                                                int NH, int NHslots, int NE, const float* const* hsrc, const float* const* esrc,
+                                                int b, int y0)
 {
-    const int lane = threadIdx.x & 31;
-    const unsigned slot = rg.idx % cfg.R, use = rg.idx / cfg.R;
-    const uint32_t full = rg.full0 + 8 * slot, empty = rg.empty0 + 8 * slot;
-    const uint32_t row_bytes = (uint32_t)cfg.pitch * 4u;
-    const int hrows = cfg.TY + 2;
-    const int total = NH * hrows + (interior ? NE * cfg.TY : 0);
-    if (lane == 0) mbar_wait(empty, (use & 1u) ^ 1u);
-    __syncwarp();
-    const float* src[4]; uint32_t dst[4]; int cnt = 0;
+    const int lane = threadIdx.x & 31, hrows = cfg.TY + 2;
+    pu.hmask = pu.emask = 0;
+    int ch = 0, ce = 0;
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
-        src[it] = nullptr; dst[it] = 0;
         const int r = lane + 32 * it;
-        if (r < total) {
-            int arr, j, yy; const float* base;
-            if (r < NH * hrows) { arr = r / hrows; j = r - arr * hrows; yy = y0 - 1 + j; base = hsrc[arr];
-                                  if (yy <= g.n[1]) {
-                                      RowRef<DIM> row = DIM == 3 ? phi_row<DIM>(g, pf, b, yy, z) : phi_row<DIM>(g, pf, b, yy, 0);
-                                      if (row.off >= 0) { src[it] = base + row.off; dst[it] = rg.stage0_s + 4u * (slot * cfg.stage_floats + (arr * hrows + j) * cfg.pitch); }
-                                  } }
-            else { const int q = r - NH * hrows; arr = q / cfg.TY; j = q - arr * cfg.TY; yy = y0 + j; base = esrc[arr];
-                   if (yy < g.n[1]) {
-                       const long long off = (long long)b * pf.sb + (DIM == 3 ? (long long)z * pf.sz : 0) + (long long)yy * pf.sy;
-                       src[it] = base + off; dst[it] = rg.stage0_s + 4u * (slot * cfg.stage_floats + (NH * hrows + arr * cfg.TY + j) * cfg.pitch);
-                   } }
+        pu.yoff[it] = 0; pu.base[it] = nullptr; pu.dsto[it] = 0;
+        if (r < NHslots * hrows) {
+            const int arr = r / hrows, j = r - arr * hrows;
+            int yy = y0 - 1 + j; float cv;
+            if (arr < NH && yy <= g.n[1] && phi_resolve(yy, pf, 1, cv)) {
+                pu.yoff[it] = (long long)b * pf.sb + (long long)yy * pf.sy;
+                pu.base[it] = hsrc[arr];
+                pu.dsto[it] = 4u * (uint32_t)((arr * hrows + j) * cfg.pitch);
+                pu.hmask |= 1u << it; ch++;
+            }
+        } else if (r < NHslots * hrows + NE * cfg.TY) {
+            const int q = r - NHslots * hrows, arr = q / cfg.TY, j = q - arr * cfg.TY;
+            const int yy = y0 + j;
+            if (yy < g.n[1]) {
+                pu.yoff[it] = (long long)b * pf.sb + (long long)yy * pf.sy;
+                pu.base[it] = esrc[arr];
+                pu.dsto[it] = 4u * (uint32_t)((NHslots * hrows + arr * cfg.TY + j) * cfg.pitch);
+                pu.emask |= 1u << it; ce++;
+            }
         }
-        cnt += src[it] != nullptr;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0) { if (cnt > 0) mbar_expect_tx(full, (uint32_t)cnt * row_bytes); else mbar_arrive(full); }
+    for (int o = 16; o > 0; o >>= 1) { ch += __shfl_xor_sync(0xffffffffu, ch, o); ce += __shfl_xor_sync(0xffffffffu, ce, o); }
+    pu.tot_h = ch; pu.tot_e = ce;
+}
+
+template <int DIM>
+__device__ __forceinline__ void ring_produce(Ring& rg, const RingCfg& cfg, const DField& pf, const ProdUnit& pu, int z, bool interior)
+{
+    const int lane = threadIdx.x & 31;
+    const int slot = rg.pos.slot;
+    const uint32_t full = rg.full0 + 8 * slot;
+    const uint32_t row_bytes = (uint32_t)cfg.pitch * 4u;
+    const uint32_t sbase = rg.stage0_s + 4u * (uint32_t)(slot * cfg.stage_floats);
+    float cv;
+    bool zmem = true;
+    if (DIM == 3) zmem = phi_resolve(z, pf, 2, cv); else z = 0;
+    const long long zoff = (long long)z * pf.sz;
+    unsigned mask = (zmem ? pu.hmask : 0u) | (interior ? pu.emask : 0u);
+    const int cnt = (zmem ? pu.tot_h : 0) + (interior ? pu.tot_e : 0);
+    if (lane == 0) {
+        mbar_wait(rg.empty0 + 8 * slot, rg.pos.par ^ 1u);
+        if (cnt > 0) mbar_expect_tx(full, (uint32_t)cnt * row_bytes); else mbar_arrive(full);
+    }
     __syncwarp();
 #pragma unroll
     for (int it = 0; it < 4; ++it)
-        if (src[it]) bulk_g2s(dst[it], src[it], row_bytes, full);
-    rg.idx++;
+        if (mask & (1u << it)) bulk_g2s(sbase + pu.dsto[it], pu.base[it] + pu.yoff[it] + zoff, row_bytes, full);
+    rg.pos.next(cfg.R);
 }
 
-__device__ __forceinline__ void ring_wait_full(const Ring& rg, const RingCfg& cfg, unsigned idx)
-{ mbar_wait(rg.full0 + 8 * (idx % cfg.R), (idx / cfg.R) & 1u); }
-
-__device__ __forceinline__ void ring_release(const Ring& rg, const RingCfg& cfg, unsigned idx)
+__device__ __forceinline__ void ring_wait_full(const Ring& rg, const SlotIt& s) { mbar_wait(rg.full0 + 8 * s.slot, s.par); }
+__device__ __forceinline__ void ring_release(const Ring& rg, const SlotIt& s)
 {
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(rg.empty0 + 8 * (idx % cfg.R));
+    if ((threadIdx.x & 31) == 0) mbar_arrive(rg.empty0 + 8 * s.slot);
+}
+__device__ __forceinline__ const float* ring_ptr(const Ring& rg, const RingCfg& cfg, const SlotIt& s)
+{ return rg.stage0 + (size_t)s.slot * cfg.stage_floats; }
+
+// ---- consumer geometry --------------------------------------------------------------------------------------------------
+#define GF_VALID 1u
+#define GF_XLO   2u     // group holds x = 0
+#define GF_XHI   4u     // group holds the last cell of the line
+#define GF_YLOC  8u     // y-1 neighbour is a constant ghost
+#define GF_YHIC  16u    // y+1 neighbour is a constant ghost
+
+struct ThreadGroups {
+    int soff[RING_G];       // float offset of the group inside a haloed array of a stage: (j+1)*pitch + x0
+    int eoff[RING_G];       // float offset inside an element-wise array of a stage: j*pitch + x0
+    int goff[RING_G];       // element offset relative to (y0, x=0) of the plane: j*sy + x0
+    int j[RING_G];
+    int xlo[RING_G], xro[RING_G];   // where the x-1 / x+4 neighbour lives in the staged line (ghosts resolved), fast path
+    unsigned needl, needr;  // bit k: the neighbour of group k cannot come from a shuffle (warp edge or line end)
+    unsigned flags[RING_G]; // per tile
+    bool fast_ok;           // kernel-level eligibility of the branch-free path
+};
+
+__device__ __forceinline__ void groups_init(ThreadGroups& tg, const RingCfg& cfg, const DGrid& g, const DField& pf)
+{
+    const int lane = threadIdx.x & 31, nx = g.n[0];
+    tg.needl = tg.needr = 0;
+#pragma unroll
+    for (int k = 0; k < RING_G; ++k) {
+        const int gi = threadIdx.x + k * RING_CONSUMERS;
+        const int j = gi / cfg.nx4, x0 = (gi - j * cfg.nx4) * 4;
+        tg.j[k] = (k < cfg.groups && j < cfg.TY && x0 < nx) ? j : -1;
+        tg.soff[k] = (j + 1) * cfg.pitch + x0;
+        tg.eoff[k] = j * cfg.pitch + x0;
+        tg.goff[k] = j * (int)pf.sy + x0;
+        tg.flags[k] = 0;
+        const int row = (j + 1) * cfg.pitch;
+        tg.xlo[k] = tg.soff[k] - 1; tg.xro[k] = tg.soff[k] + 4;
+        if (lane == 0) tg.needl |= 1u << k;
+        if (lane == 31) tg.needr |= 1u << k;
+        if (x0 == 0) { tg.needl |= 1u << k; tg.xlo[k] = pf.klo[0] == PHI_BC_PERIODIC ? row + nx - 1 : row; }
+        if (x0 + 4 >= nx) { tg.needr |= 1u << k; tg.xro[k] = pf.khi[0] == PHI_BC_PERIODIC ? row : row + nx - 1; }
+    }
+    tg.fast_ok = cfg.shfl_ok && (cfg.nx4 * 4 == nx) && (cfg.TY * cfg.nx4 == cfg.groups * RING_CONSUMERS)
+                 && pf.klo[0] != PHI_BC_CONST && pf.khi[0] != PHI_BC_CONST;
 }
 
-__device__ __forceinline__ const float* ring_slot(const Ring& rg, const RingCfg& cfg, unsigned idx)
-{ return rg.stage0 + (size_t)(idx % cfg.R) * cfg.stage_floats; }
+__device__ __forceinline__ void groups_tile(ThreadGroups& tg, const RingCfg& cfg, const DGrid& g, const DField& pf, int y0)
+{
+    const int nx = g.n[0], ny = g.n[1];
+#pragma unroll
+    for (int k = 0; k < RING_G; ++k) {
+        unsigned f = 0;
+        if (tg.j[k] >= 0) {
+            const int y = y0 + tg.j[k];
+            const int x0 = tg.eoff[k] - tg.j[k] * cfg.pitch;
+            if (y < ny) {
+                f = GF_VALID;
+                if (x0 == 0) f |= GF_XLO;
+                if (x0 + 4 >= nx) f |= GF_XHI;
+                if (y == 0 && pf.klo[1] == PHI_BC_CONST) f |= GF_YLOC;
+                if (y == ny - 1 && pf.khi[1] == PHI_BC_CONST) f |= GF_YHIC;
+            }
+        }
+        tg.flags[k] = f;
+    }
+}
 
 // ---- consumer: one plane of one tile ---------------------------------------------------------------------------------
-// sm/sc/sp: slots holding planes z-1, z, z+1 (sm/sp unused in 2-D).  Values of the differenced array are h0 (+ beta*h1).
+// sm/sc/sp: stages holding planes z-1, z, z+1 (sm/sp unused in 2-D).  Values of the differenced array are h0 (+ beta*h1).
 template <int DIM, int NH, int NE, class Epi>
-__device__ __forceinline__ void ring_compute(const RingCfg& cfg, const DGrid& g, const DField& pf,
+__device__ __forceinline__ void ring_compute(const RingCfg& cfg, const DGrid& g, const DField& pf, const ThreadGroups& tg,
                                              const float* sm, const float* sc, const float* sp, float beta,
-                                             int b, int y0, int z, Epi& epi)
+                                             long long plane_off, int z, Epi& epi)
 {
-    const int pitch = cfg.pitch, hrows = cfg.TY + 2;
-    const int total = cfg.TY * cfg.nx4;
-    const int nx = g.n[0], ny = g.n[1];
-    const int h1 = hrows * pitch;                        // offset of the second haloed array inside a stage
-    const int e0off = NH * hrows * pitch;
+    const int pitch = cfg.pitch;
+    const int h1 = (cfg.TY + 2) * pitch;                 // offset of the second haloed array inside a stage
+    const int e0off = NH * (cfg.TY + 2) * pitch;
+    const int e1off = e0off + cfg.TY * pitch;
     const float ix2 = g.inv_dx2[0], iy2 = g.inv_dx2[1], iz2 = g.inv_dx2[2];
-    const bool zm_const = DIM == 3 && z - 1 < 0 && pf.klo[2] == PHI_BC_CONST;
-    const bool zp_const = DIM == 3 && z + 1 > g.n[2] - 1 && pf.khi[2] == PHI_BC_CONST;
+    const bool zm_const = DIM == 3 && z == 0 && pf.klo[2] == PHI_BC_CONST;
+    const bool zp_const = DIM == 3 && z == g.n[2] - 1 && pf.khi[2] == PHI_BC_CONST;
     const bool use1 = NH == 2 && beta != 0.f;
+    const int lane = threadIdx.x & 31;
 
     auto val4 = [&](const float* s, int off) -> float4 {
         float4 a = *reinterpret_cast<const float4*>(s + off);
         if (use1) { const float4 o = *reinterpret_cast<const float4*>(s + h1 + off);
-                    a.x += beta * o.x; a.y += beta * o.y; a.z += beta * o.z; a.w += beta * o.w; }
+                    a.x = fmaf(beta, o.x, a.x); a.y = fmaf(beta, o.y, a.y); a.z = fmaf(beta, o.z, a.z); a.w = fmaf(beta, o.w, a.w); }
         return a;
     };
     auto val1 = [&](const float* s, int off) -> float {
         float a = s[off];
-        if (use1) a += beta * s[h1 + off];
+        if (use1) a = fmaf(beta, s[h1 + off], a);
         return a;
     };
 
-    for (int gi = threadIdx.x; gi < total; gi += RING_CONSUMERS) {
-        const int j = gi / cfg.nx4, x4 = gi - j * cfg.nx4;
-        const int y = y0 + j, x0 = x4 * 4;
-        if (y >= ny || x0 >= nx) continue;
-        const int nvalid = min(4, nx - x0);
-        const int row = (j + 1) * pitch;
-        const int rc = row + x0;
-        const float4 c = val4(sc, rc);
-        const float4 ym = (y - 1 < 0 && pf.klo[1] == PHI_BC_CONST) ? f4_splat(pf.clo[1]) : val4(sc, rc - pitch);
-        const float4 yp = (y + 1 > ny - 1 && pf.khi[1] == PHI_BC_CONST) ? f4_splat(pf.chi[1]) : val4(sc, rc + pitch);
+#pragma unroll
+    for (int k = 0; k < RING_G; ++k) {
+        const unsigned f = tg.flags[k];
+        const int rc = tg.soff[k];
+        const bool valid = (f & GF_VALID) != 0;
+        float4 c = f4_splat(0.f);
+        if (valid) c = val4(sc, rc);
         float xl, xr;
-        if (x0 > 0) xl = val1(sc, rc - 1);
-        else { const int k = pf.klo[0]; xl = k == PHI_BC_PERIODIC ? val1(sc, row + nx - 1) : (k == PHI_BC_ZERO_GRADIENT ? c.x : pf.clo[0]); }
-        if (x0 + 4 < nx) xr = val1(sc, rc + 4);
-        else { const int k = pf.khi[0]; xr = k == PHI_BC_PERIODIC ? val1(sc, row) : (k == PHI_BC_ZERO_GRADIENT ? f4_get(c, nvalid - 1) : pf.chi[0]); }
-        float4 l4 = make_float4(xl, c.x, c.y, c.z);
+        if (cfg.shfl_ok) {                                  // whole warp executes the shuffles (uniform branch)
+            xl = __shfl_up_sync(0xffffffffu, c.w, 1);
+            xr = __shfl_down_sync(0xffffffffu, c.x, 1);
+            if (valid && lane == 0 && !(f & GF_XLO)) xl = val1(sc, rc - 1);
+            if (valid && lane == 31 && !(f & GF_XHI)) xr = val1(sc, rc + 4);
+        } else if (valid) {
+            xl = (f & GF_XLO) ? 0.f : val1(sc, rc - 1);
+            xr = (f & GF_XHI) ? 0.f : val1(sc, rc + 4);
+        }
+        if (!valid) continue;
+        float4 ym, yp, q;
+        int nvalid = 4;
+        if (f == GF_VALID) {                                // interior of the line, no constant ghosts in y
+            ym = val4(sc, rc - pitch);
+            yp = val4(sc, rc + pitch);
+        } else {
+            const int row = rc - (tg.eoff[k] - tg.j[k] * pitch);          // start of the staged line
+            const int nx = g.n[0];
+            const int x0 = rc - row;
+            nvalid = min(4, nx - x0);
+            ym = (f & GF_YLOC) ? f4_splat(pf.clo[1]) : val4(sc, rc - pitch);
+            yp = (f & GF_YHIC) ? f4_splat(pf.chi[1]) : val4(sc, rc + pitch);
+            if (f & GF_XLO) { const int kx = pf.klo[0]; xl = kx == PHI_BC_PERIODIC ? val1(sc, row + nx - 1) : (kx == PHI_BC_ZERO_GRADIENT ? c.x : pf.clo[0]); }
+            if (f & GF_XHI) { const int kx = pf.khi[0]; xr = kx == PHI_BC_PERIODIC ? val1(sc, row) : (kx == PHI_BC_ZERO_GRADIENT ? f4_get(c, nvalid - 1) : pf.chi[0]); }
+        }
         float4 r4 = make_float4(c.y, c.z, c.w, xr);
         if (nvalid < 4) f4_set(r4, nvalid - 1, xr);
-        float4 q;
-        q.x = (l4.x + r4.x - 2.f * c.x) * ix2 + (ym.x + yp.x - 2.f * c.x) * iy2;
-        q.y = (l4.y + r4.y - 2.f * c.y) * ix2 + (ym.y + yp.y - 2.f * c.y) * iy2;
-        q.z = (l4.z + r4.z - 2.f * c.z) * ix2 + (ym.z + yp.z - 2.f * c.z) * iy2;
-        q.w = (l4.w + r4.w - 2.f * c.w) * ix2 + (ym.w + yp.w - 2.f * c.w) * iy2;
+        q.x = (xl + r4.x - 2.f * c.x) * ix2 + (ym.x + yp.x - 2.f * c.x) * iy2;
+        q.y = (c.x + r4.y - 2.f * c.y) * ix2 + (ym.y + yp.y - 2.f * c.y) * iy2;
+        q.z = (c.y + r4.z - 2.f * c.z) * ix2 + (ym.z + yp.z - 2.f * c.z) * iy2;
+        q.w = (c.z + r4.w - 2.f * c.w) * ix2 + (ym.w + yp.w - 2.f * c.w) * iy2;
         if (DIM == 3) {
             const float4 zm = zm_const ? f4_splat(pf.clo[2]) : val4(sm, rc);
             const float4 zp = zp_const ? f4_splat(pf.chi[2]) : val4(sp, rc);
@@ -198,11 +316,73 @@ __device__ __forceinline__ void ring_compute(const RingCfg& cfg, const DGrid& g,
             q.w += (zm.w + zp.w - 2.f * c.w) * iz2;
         }
         float4 e0 = f4_splat(0.f), e1 = f4_splat(0.f);
-        if (NE >= 1) e0 = *reinterpret_cast<const float4*>(sc + e0off + j * pitch + x0);
-        if (NE >= 2) e1 = *reinterpret_cast<const float4*>(sc + e0off + (cfg.TY + j) * pitch + x0);
-        const long long off = (long long)b * pf.sb + (DIM == 3 ? (long long)z * pf.sz : 0) + (long long)y * pf.sy + x0;
-        epi(off, c, q, nvalid, e0, e1);
+        if (NE >= 1) e0 = *reinterpret_cast<const float4*>(sc + e0off + tg.eoff[k]);
+        if (NE >= 2) e1 = *reinterpret_cast<const float4*>(sc + e1off + tg.eoff[k]);
+        epi(plane_off + tg.goff[k], c, q, nvalid, e0, e1);
     }
+}
+
+// Branch-free variant for tiles that lie completely inside the grid in y, planes without constant z ghosts and
+// non-constant x boundaries: every thread owns exactly G full groups.
+template <int DIM, int NH, int NE, int G, class Epi>
+__device__ __forceinline__ void ring_compute_fast(const RingCfg& cfg, const DGrid& g, const ThreadGroups& tg,
+                                                  const float* sm, const float* sc, const float* sp, float beta,
+                                                  long long plane_off, Epi& epi)
+{
+    const int pitch = cfg.pitch;
+    const int h1 = (cfg.TY + 2) * pitch;
+    const int e0off = NH * (cfg.TY + 2) * pitch;
+    const int e1off = e0off + cfg.TY * pitch;
+    const float ix2 = g.inv_dx2[0], iy2 = g.inv_dx2[1], iz2 = DIM == 3 ? g.inv_dx2[2] : 0.f;
+    const float cc = 2.f * (ix2 + iy2 + iz2);
+    const bool use1 = NH == 2 && beta != 0.f;
+    auto val4 = [&](const float* s, int off) -> float4 {
+        float4 a = *reinterpret_cast<const float4*>(s + off);
+        if (use1) { const float4 o = *reinterpret_cast<const float4*>(s + h1 + off);
+                    a.x = fmaf(beta, o.x, a.x); a.y = fmaf(beta, o.y, a.y); a.z = fmaf(beta, o.z, a.z); a.w = fmaf(beta, o.w, a.w); }
+        return a;
+    };
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+        const int rc = tg.soff[k];
+        const float4 c = val4(sc, rc);
+        const float4 ym = val4(sc, rc - pitch);
+        const float4 yp = val4(sc, rc + pitch);
+        float xl = __shfl_up_sync(0xffffffffu, c.w, 1);
+        float xr = __shfl_down_sync(0xffffffffu, c.x, 1);
+        if (tg.needl & (1u << k)) { xl = sc[tg.xlo[k]]; if (use1) xl = fmaf(beta, sc[h1 + tg.xlo[k]], xl); }
+        if (tg.needr & (1u << k)) { xr = sc[tg.xro[k]]; if (use1) xr = fmaf(beta, sc[h1 + tg.xro[k]], xr); }
+        float4 q;
+        q.x = fmaf(ix2, xl + c.y, fmaf(iy2, ym.x + yp.x, -cc * c.x));
+        q.y = fmaf(ix2, c.x + c.z, fmaf(iy2, ym.y + yp.y, -cc * c.y));
+        q.z = fmaf(ix2, c.y + c.w, fmaf(iy2, ym.z + yp.z, -cc * c.z));
+        q.w = fmaf(ix2, c.z + xr, fmaf(iy2, ym.w + yp.w, -cc * c.w));
+        if (DIM == 3) {
+            const float4 zm = val4(sm, rc);
+            const float4 zp = val4(sp, rc);
+            q.x = fmaf(iz2, zm.x + zp.x, q.x);
+            q.y = fmaf(iz2, zm.y + zp.y, q.y);
+            q.z = fmaf(iz2, zm.z + zp.z, q.z);
+            q.w = fmaf(iz2, zm.w + zp.w, q.w);
+        }
+        float4 e0 = f4_splat(0.f), e1 = f4_splat(0.f);
+        if (NE >= 1) e0 = *reinterpret_cast<const float4*>(sc + e0off + tg.eoff[k]);
+        if (NE >= 2) e1 = *reinterpret_cast<const float4*>(sc + e1off + tg.eoff[k]);
+        epi(plane_off + tg.goff[k], c, q, 4, e0, e1);
+    }
+}
+
+template <bool GENERIC, int DIM, int NH, int NE, class Epi>
+__device__ __forceinline__ void ring_compute_any(const RingCfg& cfg, const DGrid& g, const DField& pf, const ThreadGroups& tg,
+                                                 bool fast, const float* sm, const float* sc, const float* sp, float beta,
+                                                 long long plane_off, int z, Epi& epi)
+{
+    if (!GENERIC || fast) {
+        if (cfg.groups == 4) { ring_compute_fast<DIM, NH, NE, 4>(cfg, g, tg, sm, sc, sp, beta, plane_off, epi); return; }
+        if (cfg.groups == 2) { ring_compute_fast<DIM, NH, NE, 2>(cfg, g, tg, sm, sc, sp, beta, plane_off, epi); return; }
+        if (cfg.groups == 1) { ring_compute_fast<DIM, NH, NE, 1>(cfg, g, tg, sm, sc, sp, beta, plane_off, epi); return; }
+    }
+    if (GENERIC) ring_compute<DIM, NH, NE>(cfg, g, pf, tg, sm, sc, sp, beta, plane_off, z, epi);
 }
 
 // ---- one unit: producer streams its planes, consumers march through them --------------------------------------------------
@@ -214,45 +394,60 @@ __device__ __forceinline__ RingUnit ring_unit(const RingCfg& cfg, const DGrid& g
     RingUnit u;
     u.b = unit / cfg.units_per_batch;
     const int r = unit - u.b * cfg.units_per_batch;
-    if (DIM == 3) { const int yt = r % cfg.nyt, zc = r / cfg.nyt; u.y0 = yt * cfg.TY; u.z0 = zc * cfg.ZC; u.z1 = min(g.n[2], u.z0 + cfg.ZC); }
+    if (DIM == 3) { const int zc = r / cfg.nyt, yt = r - zc * cfg.nyt; u.y0 = yt * cfg.TY; u.z0 = zc * cfg.ZC; u.z1 = min(g.n[2], u.z0 + cfg.ZC); }
     else { u.y0 = r * cfg.TY; u.z0 = 0; u.z1 = 1; }
     return u;
 }
 
-template <int DIM, int NH, int NE, class Epi>
+template <bool GENERIC, int DIM, int NH, int NE, class Epi>
 __device__ __forceinline__ void ring_process_unit(Ring& rg, const RingCfg& cfg, const DGrid& g, const DField& pf,
+                                                  ThreadGroups& tg,
                                                   const float* const* hsrc, const float* const* esrc, float beta,
                                                   const RingUnit& u, Epi& epi)
 {
     const bool producer = threadIdx.x >= RING_CONSUMERS;
-    const int nh = (NH == 2 && beta == 0.f) ? 1 : NH;              // first CG iteration: d' = r, old direction not read
+    if (producer) {
+        const int nh = (NH == 2 && beta == 0.f) ? 1 : NH;          // first CG iteration: d' = r, old direction not read
+        ProdUnit pu;
+        prod_unit_setup<DIM>(pu, cfg, g, pf, nh, NH, NE, hsrc, esrc, u.b, u.y0);
+        if (DIM == 3) {
+            const int nz = u.z1 - u.z0;
+            for (int p = 0; p < nz + 2; ++p)
+                ring_produce<DIM>(rg, cfg, pf, pu, u.z0 - 1 + p, p >= 1 && p <= nz);
+        } else {
+            ring_produce<DIM>(rg, cfg, pf, pu, 0, true);
+        }
+        return;
+    }
+    const int ny = g.n[1];
+    const bool tile_fast = !GENERIC || tg.fast_ok && u.y0 + cfg.TY <= ny
+                           && !(u.y0 == 0 && pf.klo[1] == PHI_BC_CONST) && !(u.y0 + cfg.TY == ny && pf.khi[1] == PHI_BC_CONST);
+    if (GENERIC && !tile_fast) groups_tile(tg, cfg, g, pf, u.y0);
+    long long plane_off = (long long)u.b * pf.sb + (long long)u.y0 * pf.sy + (DIM == 3 ? (long long)u.z0 * pf.sz : 0);
     if (DIM == 3) {
         const int nz = u.z1 - u.z0;
-        if (producer) {
-            for (int p = 0; p < nz + 2; ++p)
-                ring_produce<DIM>(rg, cfg, g, pf, nh, NE, hsrc, esrc, u.b, u.y0, u.z0 - 1 + p, p >= 1 && p <= nz);
-        } else {
-            const unsigned base = rg.idx;
-            ring_wait_full(rg, cfg, base); ring_wait_full(rg, cfg, base + 1);
-            for (int zi = 0; zi < nz; ++zi) {
-                ring_wait_full(rg, cfg, base + zi + 2);
-                ring_compute<DIM, NH, NE>(cfg, g, pf, ring_slot(rg, cfg, base + zi), ring_slot(rg, cfg, base + zi + 1),
-                                          ring_slot(rg, cfg, base + zi + 2), beta, u.b, u.y0, u.z0 + zi, epi);
-                ring_release(rg, cfg, base + zi);
-            }
-            ring_release(rg, cfg, base + nz); ring_release(rg, cfg, base + nz + 1);
-            rg.idx = base + nz + 2;
+        SlotIt a = rg.pos, bq = a; bq.next(cfg.R);
+        SlotIt c2 = bq; c2.next(cfg.R);
+        ring_wait_full(rg, a); ring_wait_full(rg, bq);
+        for (int zi = 0; zi < nz; ++zi) {
+            const int z = u.z0 + zi;
+            const bool fast = tile_fast && !(z == 0 && pf.klo[2] == PHI_BC_CONST) && !(z == g.n[2] - 1 && pf.khi[2] == PHI_BC_CONST);
+            ring_wait_full(rg, c2);
+            ring_compute_any<GENERIC, DIM, NH, NE>(cfg, g, pf, tg, fast, ring_ptr(rg, cfg, a), ring_ptr(rg, cfg, bq), ring_ptr(rg, cfg, c2),
+                                          beta, plane_off, z, epi);
+            ring_release(rg, a);
+            a = bq; bq = c2; c2.next(cfg.R);
+            plane_off += pf.sz;
         }
+        ring_release(rg, a); ring_release(rg, bq);
+        rg.pos = c2;
     } else {
-        if (producer) ring_produce<DIM>(rg, cfg, g, pf, nh, NE, hsrc, esrc, u.b, u.y0, 0, true);
-        else {
-            const unsigned base = rg.idx;
-            ring_wait_full(rg, cfg, base);
-            const float* sc = ring_slot(rg, cfg, base);
-            ring_compute<DIM, NH, NE>(cfg, g, pf, sc, sc, sc, beta, u.b, u.y0, 0, epi);
-            ring_release(rg, cfg, base);
-            rg.idx = base + 1;
-        }
+        const SlotIt a = rg.pos;
+        ring_wait_full(rg, a);
+        const float* sc = ring_ptr(rg, cfg, a);
+        ring_compute_any<GENERIC, DIM, NH, NE>(cfg, g, pf, tg, tile_fast, sc, sc, sc, beta, plane_off, 0, epi);
+        ring_release(rg, a);
+        rg.pos.next(cfg.R);
     }
 }
 
@@ -311,19 +506,21 @@ struct REpiPassB {              // e0 = x, e1 = r
 };
 
 // ---- laplace -----------------------------------------------------------------------------------------------------------
-template <int DIM, bool AXPY>
-__global__ void __launch_bounds__(RING_THREADS, 1)
+template <int DIM, bool AXPY, bool GENERIC>
+__global__ void __launch_bounds__(RING_THREADS, 2)
 k_laplace_ring(DGrid g, DField f, RingCfg cfg, const float* __restrict__ x, float* __restrict__ y, float coeff)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     Ring rg;
     ring_init(rg, smem, cfg);
+    ThreadGroups tg;
+    groups_init(tg, cfg, g, f);
     const float* hsrc[2] = {x, nullptr};
     const float* esrc[2] = {nullptr, nullptr};
     REpiLaplace<AXPY> epi{y, coeff};
     for (int unit = blockIdx.x; unit < cfg.total_units; unit += gridDim.x) {
         const RingUnit u = ring_unit<DIM>(cfg, g, unit);
-        ring_process_unit<DIM, 1, 0>(rg, cfg, g, f, hsrc, esrc, 0.f, u, epi);
+        ring_process_unit<GENERIC, DIM, 1, 0>(rg, cfg, g, f, tg, hsrc, esrc, 0.f, u, epi);
     }
 }
 
@@ -335,21 +532,22 @@ struct CgRingArgs {
 };
 
 template <int DIM, class F>
-__device__ __forceinline__ void ring_unit_cells(const RingCfg& cfg, const DGrid& g, const DField& pf, const RingUnit& u, F&& fn)
+__device__ __forceinline__ void ring_unit_cells(const RingCfg& cfg, const DGrid& g, const DField& pf, const ThreadGroups& tg,
+                                                const RingUnit& u, F&& fn)
 {
     // plain element-wise traversal of a unit by the consumer threads (sums, mean removal); no staging
     if (threadIdx.x >= RING_CONSUMERS) return;
-    const int total = cfg.TY * cfg.nx4;
-    for (int z = u.z0; z < u.z1; ++z)
-        for (int gi = threadIdx.x; gi < total; gi += RING_CONSUMERS) {
-            const int j = gi / cfg.nx4, x0 = (gi - j * cfg.nx4) * 4, y = u.y0 + j;
-            if (y >= g.n[1] || x0 >= g.n[0]) continue;
-            const long long off = (long long)u.b * pf.sb + (DIM == 3 ? (long long)z * pf.sz : 0) + (long long)y * pf.sy + x0;
-            fn(off, min(4, g.n[0] - x0));
+    long long plane_off = (long long)u.b * pf.sb + (long long)u.y0 * pf.sy + (DIM == 3 ? (long long)u.z0 * pf.sz : 0);
+    for (int z = u.z0; z < u.z1; ++z, plane_off += pf.sz)
+#pragma unroll
+        for (int k = 0; k < RING_G; ++k) {
+            if (tg.j[k] < 0 || u.y0 + tg.j[k] >= g.n[1]) continue;
+            const int x0 = tg.eoff[k] - tg.j[k] * cfg.pitch;
+            fn(plane_off + tg.goff[k], min(4, g.n[0] - x0));
         }
 }
 
-template <int DIM>
+template <int DIM, bool GENERIC>
 __global__ void __launch_bounds__(RING_THREADS, 1)
 k_cg_ring(CgRingArgs A)
 {
@@ -365,6 +563,8 @@ k_cg_ring(CgRingArgs A)
     const double cells = (double)g.n[0] * g.n[1] * g.n[2];
     const float coffs = a.prm.matrix_offset;
     int region = 0;
+    ThreadGroups tg;
+    groups_init(tg, cfg, g, a.pf);
 
     auto sweep = [&](const unsigned char* active, auto&& body) {
         int cur_b = -1; float acc0 = 0.f, acc1 = 0.f;
@@ -392,7 +592,7 @@ k_cg_ring(CgRingArgs A)
 
     if (a.prm.balance_rhs || coffs != 0.f) {
         sweep(nullptr, [&](const RingUnit& u, float& acc0, float& acc1) {
-            ring_unit_cells<DIM>(cfg, g, a.pf, u, [&](long long off, int nvalid) {
+            ring_unit_cells<DIM>(cfg, g, a.pf, tg, u, [&](long long off, int nvalid) {
                 for (int j = 0; j < nvalid; ++j) { acc0 += a.rhs[off + j]; acc1 += a.x[off + j]; }
             });
         });
@@ -409,7 +609,7 @@ k_cg_ring(CgRingArgs A)
         const float* esrc[2] = {a.rhs, nullptr};
         sweep(nullptr, [&](const RingUnit& u, float& acc0, float& acc1) {
             REpiResidual0 epi{a.r, sh.mean[u.b], sh.offs[u.b], 0.f, 0.f};
-            ring_process_unit<DIM, 1, 1>(rg, cfg, g, a.pf, hsrc, esrc, 0.f, u, epi);
+            ring_process_unit<GENERIC, DIM, 1, 1>(rg, cfg, g, a.pf, tg, hsrc, esrc, 0.f, u, epi);
             acc0 += epi.acc0; acc1 += epi.acc1;
         });
     }
@@ -436,7 +636,7 @@ k_cg_ring(CgRingArgs A)
             const float* esrc[2] = {nullptr, nullptr};
             sweep(sh.cont, [&](const RingUnit& u, float& acc0, float& acc1) {
                 REpiPassA epi{dnew, 0.f, 0.f};
-                ring_process_unit<DIM, 2, 0>(rg, cfg, g, a.pf, hsrc, esrc, sh.beta[u.b], u, epi);
+                ring_process_unit<GENERIC, DIM, 2, 0>(rg, cfg, g, a.pf, tg, hsrc, esrc, sh.beta[u.b], u, epi);
                 acc0 += epi.acc0; acc1 += epi.acc1;
             });
         }
@@ -454,7 +654,7 @@ k_cg_ring(CgRingArgs A)
             const float* esrc[2] = {a.x, a.r};
             sweep(sh.cont, [&](const RingUnit& u, float& acc0, float& acc1) {
                 REpiPassB epi{a.x, a.r, sh.alpha[u.b], sh.offs[u.b], 0.f, 0.f};
-                ring_process_unit<DIM, 1, 2>(rg, cfg, g, a.pf, hsrc, esrc, 0.f, u, epi);
+                ring_process_unit<GENERIC, DIM, 1, 2>(rg, cfg, g, a.pf, tg, hsrc, esrc, 0.f, u, epi);
                 acc0 += epi.acc0;
             });
         }
@@ -480,7 +680,7 @@ k_cg_ring(CgRingArgs A)
 
     if (a.prm.project_mean) {
         sweep(nullptr, [&](const RingUnit& u, float& acc0, float& acc1) {
-            ring_unit_cells<DIM>(cfg, g, a.pf, u, [&](long long off, int nvalid) {
+            ring_unit_cells<DIM>(cfg, g, a.pf, tg, u, [&](long long off, int nvalid) {
                 for (int j = 0; j < nvalid; ++j) acc0 += a.x[off + j];
             });
         });
@@ -488,7 +688,7 @@ k_cg_ring(CgRingArgs A)
         for (int unit = blockIdx.x; unit < cfg.total_units; unit += gridDim.x) {
             const RingUnit u = ring_unit<DIM>(cfg, g, unit);
             const float m = (float)(sh.sum0[u.b] / cells);
-            ring_unit_cells<DIM>(cfg, g, a.pf, u, [&](long long off, int nvalid) {
+            ring_unit_cells<DIM>(cfg, g, a.pf, tg, u, [&](long long off, int nvalid) {
                 for (int j = 0; j < nvalid; ++j) a.x[off + j] -= m;
             });
         }
@@ -507,22 +707,25 @@ k_cg_ring(CgRingArgs A)
 // ---- host side ------------------------------------------------------------------------------------------------------------
 static const int kSmemBudget = 227 * 1024;
 
-// rows_per_ty(TY) = lines staged per stage; returns false when the grid lines are too long for a useful ring
+// lines staged per stage = lines_a * TY + lines_b; returns false when the grid lines are too long for a useful ring
 static bool ring_config(const DGrid& g, int lines_a, int lines_b, int reserve_bytes, int min_stages, int max_stages,
                         int target_units, RingCfg* out)
 {
     RingCfg c;
     c.pitch = g.cext[0]; c.nx4 = g.cext[0] / 4;
     const int row_bytes = c.pitch * 4;
-    const int ty_max = g.dim == 3 ? 8 : 16;
-    int ty = ty_max;
+    int ty = g.dim == 3 ? 8 : 16;
     for (;; ty /= 2) {
         if (ty < 1) return false;
-        const int stage_bytes = (lines_a * ty + lines_b) * row_bytes;          // lines = lines_a*TY + lines_b
+        if (ty * c.nx4 > RING_G * RING_CONSUMERS) continue;                    // <= RING_G groups per thread
+        if (lines_a * ty + lines_b > 128) continue;                            // <= 4 lines per producer lane
+        const int stage_bytes = (lines_a * ty + lines_b) * row_bytes;
         const int r = (kSmemBudget - reserve_bytes - 128) / stage_bytes;
         if (r >= min_stages) { c.TY = ty; c.R = r > max_stages ? max_stages : r; c.stage_floats = stage_bytes / 4; break; }
     }
-    while (c.TY > 1 && c.TY / 2 >= g.n[1] && g.dim == 2) c.TY /= 2;
+    while (g.dim == 2 && c.TY > 1 && c.TY / 2 >= g.n[1]) c.TY /= 2;
+    c.groups = (c.TY * c.nx4 + RING_CONSUMERS - 1) / RING_CONSUMERS;
+    c.shfl_ok = (c.nx4 % 32 == 0) ? 1 : 0;
     if (g.dim == 3) {
         c.nyt = (g.n[1] + c.TY - 1) / c.TY;
         int zc = g.n[2] < 64 ? g.n[2] : 64;
@@ -539,6 +742,14 @@ static bool ring_config(const DGrid& g, int lines_a, int lines_b, int reserve_by
     }
     *out = c;
     return true;
+}
+
+// every tile and plane of the grid qualifies for the branch-free consumer path
+static bool ring_all_fast(const DGrid& g, const DField& f, const RingCfg& c)
+{
+    if (!c.shfl_ok || c.nx4 * 4 != g.n[0] || c.TY * c.nx4 != c.groups * RING_CONSUMERS || g.n[1] % c.TY != 0) return false;
+    for (int a = 0; a < g.dim; ++a) if (f.klo[a] == PHI_BC_CONST || f.khi[a] == PHI_BC_CONST) return false;
+    return c.groups == 1 || c.groups == 2 || c.groups == 4;
 }
 
 static int sm_count()
@@ -560,11 +771,14 @@ int phi_launch_laplace_ring(const DGrid& g, const DField& f, const float* x, flo
     int grid = sms * 2;
     if (grid > cfg.total_units) grid = cfg.total_units;
     cudaError_t e;
-#define LAUNCH_LAP(D, AX) do { \
-        e = cudaFuncSetAttribute(k_laplace_ring<D, AX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e == cudaSuccess) k_laplace_ring<D, AX><<<grid, RING_THREADS, smem, s>>>(g, f, cfg, x, y, coeff); } while (0)
-    if (g.dim == 3) { if (axpy) LAUNCH_LAP(3, true); else LAUNCH_LAP(3, false); }
-    else            { if (axpy) LAUNCH_LAP(2, true); else LAUNCH_LAP(2, false); }
+    const bool generic = !ring_all_fast(g, f, cfg);
+#define LAUNCH_LAP(D, AX, GEN) do { \
+        e = cudaFuncSetAttribute(k_laplace_ring<D, AX, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e == cudaSuccess) k_laplace_ring<D, AX, GEN><<<grid, RING_THREADS, smem, s>>>(g, f, cfg, x, y, coeff); } while (0)
+#define LAUNCH_LAP2(D, AX) do { if (generic) LAUNCH_LAP(D, AX, true); else LAUNCH_LAP(D, AX, false); } while (0)
+    if (g.dim == 3) { if (axpy) LAUNCH_LAP2(3, true); else LAUNCH_LAP2(3, false); }
+    else            { if (axpy) LAUNCH_LAP2(2, true); else LAUNCH_LAP2(2, false); }
+#undef LAUNCH_LAP2
 #undef LAUNCH_LAP
     if (e != cudaSuccess) return (int)e;
     return (int)cudaGetLastError();
@@ -582,13 +796,11 @@ int phi_launch_cg_ring(const CgLaunch& l, cudaStream_t s)
     const size_t smem = (size_t)cgs + 128 + (size_t)A.cfg.R * A.cfg.stage_floats * 4;
     int per_sm = 0;
     cudaError_t e;
-    if (g.dim == 3) {
-        e = cudaFuncSetAttribute(k_cg_ring<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_ring<3>, RING_THREADS, smem);
-    } else {
-        e = cudaFuncSetAttribute(k_cg_ring<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_ring<2>, RING_THREADS, smem);
-    }
+    const bool generic = !ring_all_fast(g, l.pf, A.cfg);
+    const void* fn = g.dim == 3 ? (generic ? (const void*)k_cg_ring<3, true> : (const void*)k_cg_ring<3, false>)
+                                : (generic ? (const void*)k_cg_ring<2, true> : (const void*)k_cg_ring<2, false>);
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, RING_THREADS, smem);
     if (e != cudaSuccess || per_sm < 1) return -100;
     int grid = sms * per_sm;
     if (grid > A.cfg.total_units) grid = A.cfg.total_units;
@@ -603,8 +815,7 @@ int phi_launch_cg_ring(const CgLaunch& l, cudaStream_t s)
     a.partials = (double*)(ws + 3 * arr);
     a.result = l.result; a.prm = l.prm;
     void* args[] = {&A};
-    if (g.dim == 3) e = cudaLaunchCooperativeKernel((void*)k_cg_ring<3>, dim3(grid), dim3(RING_THREADS), args, smem, s);
-    else            e = cudaLaunchCooperativeKernel((void*)k_cg_ring<2>, dim3(grid), dim3(RING_THREADS), args, smem, s);
+    e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(RING_THREADS), args, smem, s);
     if (e != cudaSuccess) { phi_set_error("cg ring: cooperative launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;
 }
