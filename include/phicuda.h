@@ -37,6 +37,9 @@ extern "C" {
 #define PHI_BC_CONST         0
 #define PHI_BC_ZERO_GRADIENT 1
 #define PHI_BC_PERIODIC      2
+/* Multi-GPU z-slabs only: the side borders another rank's slab.  Neighbour values are read from the `halo` planes that
+ * the caller allocated around the owned range and keeps up to date (halo exchange); faces are stored as for PERIODIC. */
+#define PHI_BC_HALO          3
 
 #define PHI_ERR_INVALID   (-1)   /* bad argument (message says which) */
 #define PHI_ERR_UNSUPPORTED (-2) /* valid in the reference but outside this fast path: caller must fall through */
@@ -49,6 +52,8 @@ typedef struct PhiGrid {
     int32_t cext[3];    /* allocated extent of centred arrays   (see layout above) */
     int32_t fext[3];    /* allocated extent of staggered components */
     float   dx[3];      /* cell size = bounds.size / resolution  (phi/geom/_grid.py:117-119) */
+    int32_t halo;       /* 3-D z-slabs: planes allocated below AND above the owned range n[2]; array pointers address the
+                           first OWNED plane, cext[2] = fext[2] = n[2] + 2*halo.  0 on a single GPU. */
 } PhiGrid;
 
 /* Boundary of one scalar array (a centred field or ONE component of a staggered field). */
@@ -134,6 +139,23 @@ size_t phicuda_cg_workspace_bytes(const PhiGrid* g);
 int phicuda_cg_poisson_f32(const PhiGrid* g, const PhiVBC* vbc, const float* rhs, float* x,
                            const PhiCgParams* prm, PhiCgResult* result, void* workspace, size_t workspace_bytes,
                            void* stream);
+
+/* ---- multi-GPU (one process per GPU, z-slab decomposition) ------------------------------------------
+ * The distributed solve is the SAME persistent kernel as phicuda_cg_poisson_f32; in addition every rank
+ *   - stores the first / last owned plane of the vectors it updates straight into the neighbour's halo planes through
+ *     NVLink peer pointers (the halo exchange is fused into the pass epilogues), and
+ *   - closes each dot product by writing its partial sums into every peer's mailbox and summing the mailboxes in rank
+ *     order (an all-reduce without leaving the kernel; identical results on all ranks).
+ * PhiComm owns one cudaMalloc'd buffer per rank that holds the mailboxes and the CG work vectors; the buffers are
+ * exchanged as CUDA IPC handles (64 bytes each) by the caller (e.g. with torch.distributed.all_gather). */
+typedef struct PhiComm PhiComm;
+#define PHI_IPC_HANDLE_BYTES 64
+int phicuda_comm_create(int rank, int nranks, const PhiGrid* g, PhiComm** comm, void* ipc_handle_out);
+int phicuda_comm_connect(PhiComm* comm, const void* all_handles /* nranks * 64 bytes, rank order */);
+int phicuda_comm_destroy(PhiComm* comm);
+/* g describes the LOCAL slab (boundary kind PHI_BC_HALO on interior slab faces); x must carry valid halo planes. */
+int phicuda_cg_poisson_dist_f32(const PhiGrid* g, const PhiVBC* vbc, const float* rhs, float* x,
+                                const PhiCgParams* prm, PhiCgResult* result, PhiComm* comm, void* stream);
 
 /* ---- A1  fluid.make_incompressible (phi/physics/fluid.py:94-162), no obstacles, order 2, staggered ------------------
  * div scratch: one centred array.  Equivalent to divergence + cg_poisson + grad_sub on the same stream. */

@@ -11,13 +11,13 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libphicuda.so')
 
-BC_CONST, BC_ZERO_GRADIENT, BC_PERIODIC = 0, 1, 2
+BC_CONST, BC_ZERO_GRADIENT, BC_PERIODIC, BC_HALO = 0, 1, 2, 3
 ERR_INVALID, ERR_UNSUPPORTED, ERR_WORKSPACE = -1, -2, -3
 
 
 class PhiGrid(C.Structure):
     _fields_ = [('dim', C.c_int32), ('batch', C.c_int32), ('n', C.c_int32 * 3), ('cext', C.c_int32 * 3),
-                ('fext', C.c_int32 * 3), ('dx', C.c_float * 3)]
+                ('fext', C.c_int32 * 3), ('dx', C.c_float * 3), ('halo', C.c_int32)]
 
 
 class PhiBC(C.Structure):
@@ -65,6 +65,11 @@ PROTOTYPES = {
                                          C.c_void_p, C.c_size_t, C.c_void_p]),
     'phicuda_make_incompressible_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), F3, C.c_void_p, C.c_void_p, _P(PhiCgParams),
                                                   C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'phicuda_comm_create': (C.c_int, [C.c_int, C.c_int, _P(PhiGrid), _P(C.c_void_p), C.c_void_p]),
+    'phicuda_comm_connect': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'phicuda_comm_destroy': (C.c_int, [C.c_void_p]),
+    'phicuda_cg_poisson_dist_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), C.c_void_p, C.c_void_p, _P(PhiCgParams), C.c_void_p,
+                                              C.c_void_p, C.c_void_p]),
     'phicuda_plume_scratch_bytes': (C.c_size_t, [_P(PhiGrid)]),
     'phicuda_plume_step_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), _P(PhiBC), F3, C.c_void_p, C.c_void_p, C.c_void_p,
                                          _P(PhiPlumeParams), _P(PhiCgParams), C.c_void_p, C.c_void_p, C.c_void_p,

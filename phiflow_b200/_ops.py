@@ -14,7 +14,7 @@ import torch
 from . import _lib
 from ._lib import PhiGrid, PhiBC, PhiVBC, PhiCgParams, PhiCgResult, PhiPlumeParams, F3
 
-PERIODIC, ZG = 'periodic', 'zg'
+PERIODIC, ZG, HALO = 'periodic', 'zg', 'halo'
 _RESULT_DTYPE = np.dtype([('iterations', np.int32), ('converged', np.int32), ('diverged', np.int32),
                           ('residual_sq', np.float32), ('tol_sq', np.float32), ('initial_residual_sq', np.float32)])
 
@@ -24,6 +24,8 @@ def _kind(side):
         return _lib.BC_PERIODIC
     if side == ZG:
         return _lib.BC_ZERO_GRADIENT
+    if side == HALO:
+        return _lib.BC_HALO
     return _lib.BC_CONST
 
 
@@ -49,7 +51,7 @@ def stored_faces(vspec, axis):
     """(lower stored, upper stored) - PhiML/phiml/math/extrapolation.py:57-62."""
     spec = vspec[0] if isinstance(vspec, list) else vspec
     lo, hi = spec[axis]
-    return (lo == ZG or lo == PERIODIC), (hi == ZG)
+    return (lo == ZG or lo == PERIODIC or lo == HALO), (hi == ZG)
 
 
 def require_cuda():
@@ -57,14 +59,15 @@ def require_cuda():
         raise RuntimeError("phiflow_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
 
 
-def _ptr(t: Optional[torch.Tensor]):
-    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+def _ptr(t: Optional[torch.Tensor], off: int = 0):
+    """Device address of the first OWNED plane (off = byte offset of the lower halo planes, 0 on a single GPU)."""
+    return C.c_void_p(t.data_ptr() + off) if t is not None else C.c_void_p(0)
 
 
-def _f3(ts: Sequence[torch.Tensor]):
+def _f3(ts: Sequence[torch.Tensor], off: int = 0):
     arr = F3()
     for i in range(3):
-        arr[i] = ts[i].data_ptr() if i < len(ts) else None
+        arr[i] = ts[i].data_ptr() + off if i < len(ts) else None
     return arr
 
 
@@ -75,7 +78,7 @@ def _stream():
 class Domain:
     """Resolution, cell size, batch size and the allocation extents of centred / staggered arrays (include/phicuda.h)."""
 
-    def __init__(self, resolution: Sequence[int], dx: Sequence[float], batch: int = 1, vbc=None, device='cuda'):
+    def __init__(self, resolution: Sequence[int], dx: Sequence[float], batch: int = 1, vbc=None, device='cuda', halo: int = 0):
         self.dim = len(resolution)
         assert self.dim in (2, 3), "only 2-D and 3-D grids"
         self.res = tuple(int(r) for r in resolution)
@@ -84,8 +87,13 @@ class Domain:
         self.device = torch.device(device)
         self.upper = tuple(stored_faces(vbc, a)[1] if vbc is not None else False for a in range(self.dim))
         r4 = lambda v: (v + 3) // 4 * 4
-        self.cext = (r4(self.res[0]),) + self.res[1:]
-        self.fext = (r4(self.res[0] + int(self.upper[0])),) + tuple(self.res[a] + int(self.upper[a]) for a in range(1, self.dim))
+        self.halo = int(halo)                 # z-slab halo planes on each side (multi-GPU); `resolution` is the OWNED slab
+        assert self.halo == 0 or self.dim == 3
+        pad = lambda a: 2 * self.halo if a == 2 else 0
+        self.cext = (r4(self.res[0]),) + tuple(self.res[a] + pad(a) for a in range(1, self.dim))
+        self.fext = (r4(self.res[0] + int(self.upper[0])),) + tuple(self.res[a] + int(self.upper[a]) + pad(a) for a in range(1, self.dim))
+        self.coff = 4 * self.halo * self.cext[0] * self.cext[1]       # byte offset of the first owned plane
+        self.foff = 4 * self.halo * self.fext[0] * self.fext[1]
         g = PhiGrid()
         g.dim, g.batch = self.dim, self.batch
         for a in range(3):
@@ -93,6 +101,7 @@ class Domain:
             g.cext[a] = self.cext[a] if a < self.dim else 1
             g.fext[a] = self.fext[a] if a < self.dim else 1
             g.dx[a] = self.dx[a] if a < self.dim else 1.0
+        g.halo = self.halo
         self.grid = g
         self._ws = None
         self._result = None
@@ -133,7 +142,7 @@ class Domain:
         src = torch.from_numpy(np.ascontiguousarray(np.transpose(a, (0,) + tuple(range(self.dim, 0, -1)))))
         idx = [slice(None)]
         for ax in range(self.dim - 1, -1, -1):               # device axis order: z, y, x
-            start = offset if ax == offset_axis else 0
+            start = (offset if ax == offset_axis else 0) + (self.halo if ax == 2 else 0)
             idx.append(slice(start, start + a.shape[1 + ax]))
         t[tuple(idx)] = src.to(self.device)
         return t
@@ -141,7 +150,7 @@ class Domain:
     def _to_host(self, t: torch.Tensor, shape, offset_axis=None, offset=0) -> np.ndarray:
         idx = [slice(None)]
         for ax in range(self.dim - 1, -1, -1):
-            start = offset if ax == offset_axis else 0
+            start = (offset if ax == offset_axis else 0) + (self.halo if ax == 2 else 0)
             idx.append(slice(start, start + shape[ax]))
         a = t[tuple(idx)].cpu().numpy()
         return np.ascontiguousarray(np.transpose(a, (0,) + tuple(range(self.dim, 0, -1))))
@@ -185,7 +194,7 @@ def laplace(dom: Domain, bc, x: torch.Tensor, out: torch.Tensor = None) -> torch
     """field.laplace order 2 (phi/field/_field_math.py:118-145)."""
     require_cuda()
     out = dom.alloc_centered() if out is None else out
-    _lib.check(_lib.load().phicuda_laplace_f32(C.byref(dom.grid), C.byref(make_bc(bc)), _ptr(x), _ptr(out), _stream()))
+    _lib.check(_lib.load().phicuda_laplace_f32(C.byref(dom.grid), C.byref(make_bc(bc)), _ptr(x, dom.coff), _ptr(out, dom.coff), _stream()))
     return out
 
 
@@ -193,7 +202,7 @@ def laplace_axpy(dom: Domain, bc, x, coeff: float, out=None):
     """x + coeff * laplace(x): one explicit diffusion sub-step (phi/physics/diffuse.py:13-60)."""
     require_cuda()
     out = dom.alloc_centered() if out is None else out
-    _lib.check(_lib.load().phicuda_laplace_axpy_f32(C.byref(dom.grid), C.byref(make_bc(bc)), _ptr(x), C.c_float(coeff), _ptr(out), _stream()))
+    _lib.check(_lib.load().phicuda_laplace_axpy_f32(C.byref(dom.grid), C.byref(make_bc(bc)), _ptr(x, dom.coff), C.c_float(coeff), _ptr(out, dom.coff), _stream()))
     return out
 
 
@@ -201,14 +210,14 @@ def divergence(dom: Domain, vbc, v: List[torch.Tensor], out=None):
     """field.divergence of a staggered grid (phi/field/_field_math.py:617-626)."""
     require_cuda()
     out = dom.alloc_centered() if out is None else out
-    _lib.check(_lib.load().phicuda_divergence_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(v), _ptr(out), _stream()))
+    _lib.check(_lib.load().phicuda_divergence_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(v, dom.foff), _ptr(out, dom.coff), _stream()))
     return out
 
 
 def grad_sub(dom: Domain, vbc, v: List[torch.Tensor], p: torch.Tensor):
     """v -= spatial_gradient(p, at='face') in place (phi/physics/fluid.py:158-161)."""
     require_cuda()
-    _lib.check(_lib.load().phicuda_grad_sub_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(v), _ptr(p), _stream()))
+    _lib.check(_lib.load().phicuda_grad_sub_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(v, dom.foff), _ptr(p, dom.coff), _stream()))
     return v
 
 
@@ -216,8 +225,8 @@ def advect_centered(dom: Domain, vbc, vel, fbc, src, dt: float, out=None):
     """advect.semi_lagrangian of a centred field (phi/physics/advect.py:156-179)."""
     require_cuda()
     out = dom.alloc_centered() if out is None else out
-    _lib.check(_lib.load().phicuda_advect_centered_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(vel),
-                                                       C.byref(make_bc(fbc)), _ptr(src), _ptr(out), C.c_float(dt), _stream()))
+    _lib.check(_lib.load().phicuda_advect_centered_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(vel, dom.foff),
+                                                       C.byref(make_bc(fbc)), _ptr(src, dom.coff), _ptr(out, dom.coff), C.c_float(dt), _stream()))
     return out
 
 
@@ -225,8 +234,8 @@ def advect_staggered(dom: Domain, vbc, vel, fbc, src, dt: float, out=None):
     """advect.semi_lagrangian of a staggered field (self-advection when src is vel)."""
     require_cuda()
     out = dom.alloc_faces() if out is None else out
-    _lib.check(_lib.load().phicuda_advect_staggered_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(vel),
-                                                        C.byref(make_vbc(fbc, dom.dim)), _f3(src), _f3(out), C.c_float(dt), _stream()))
+    _lib.check(_lib.load().phicuda_advect_staggered_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(vel, dom.foff),
+                                                        C.byref(make_vbc(fbc, dom.dim)), _f3(src, dom.foff), _f3(out, dom.foff), C.c_float(dt), _stream()))
     return out
 
 
@@ -235,15 +244,15 @@ def mac_cormack_centered(dom: Domain, vbc, vel, fbc, src, dt: float, correction_
     require_cuda()
     out = dom.alloc_centered() if out is None else out
     tmp = dom.alloc_centered()
-    _lib.check(_lib.load().phicuda_mac_cormack_centered_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(vel),
-                                                            C.byref(make_bc(fbc)), _ptr(src), _ptr(out), _ptr(tmp),
+    _lib.check(_lib.load().phicuda_mac_cormack_centered_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(vel, dom.foff),
+                                                            C.byref(make_bc(fbc)), _ptr(src, dom.coff), _ptr(out, dom.coff), _ptr(tmp, dom.coff),
                                                             C.c_float(dt), C.c_float(correction_strength), _stream()))
     return out
 
 
 def axpy_centered(dom: Domain, a: float, x, y):
     require_cuda()
-    _lib.check(_lib.load().phicuda_axpy_centered_f32(C.byref(dom.grid), C.c_float(a), _ptr(x), _ptr(y), _stream()))
+    _lib.check(_lib.load().phicuda_axpy_centered_f32(C.byref(dom.grid), C.c_float(a), _ptr(x, dom.coff), _ptr(y, dom.coff), _stream()))
     return y
 
 
@@ -252,7 +261,7 @@ def add_buoyancy(dom: Domain, vbc, sbc, s, factor: Sequence[float], dt: float, v
     require_cuda()
     b = (C.c_float * 3)(*[float(factor[i]) if i < len(factor) else 0.0 for i in range(3)])
     _lib.check(_lib.load().phicuda_add_buoyancy_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), C.byref(make_bc(sbc)),
-                                                    _ptr(s), b, C.c_float(dt), _f3(v), _stream()))
+                                                    _ptr(s, dom.coff), b, C.c_float(dt), _f3(v, dom.foff), _stream()))
     return v
 
 
@@ -285,7 +294,7 @@ def cg_poisson(dom: Domain, vbc, rhs, x0=None, prm: PhiCgParams = None):
     ws, res = dom.workspace()
     x = dom.alloc_centered() if x0 is None else x0
     prm = prm or cg_params(vbc)
-    _lib.check(_lib.load().phicuda_cg_poisson_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _ptr(rhs), _ptr(x), C.byref(prm),
+    _lib.check(_lib.load().phicuda_cg_poisson_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _ptr(rhs, dom.coff), _ptr(x, dom.coff), C.byref(prm),
                                                   _ptr(res), _ptr(ws), C.c_size_t(ws.numel()), _stream()))
     return x
 
@@ -297,7 +306,7 @@ def make_incompressible(dom: Domain, vbc, v, p=None, prm: PhiCgParams = None):
     p = dom.alloc_centered() if p is None else p
     div = dom.alloc_centered()
     prm = prm or cg_params(vbc)
-    _lib.check(_lib.load().phicuda_make_incompressible_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(v), _ptr(p), _ptr(div),
+    _lib.check(_lib.load().phicuda_make_incompressible_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(v, dom.foff), _ptr(p, dom.coff), _ptr(div, dom.coff),
                                                            C.byref(prm), _ptr(res), _ptr(ws), C.c_size_t(ws.numel()), _stream()))
     return v, p
 
@@ -305,6 +314,7 @@ def make_incompressible(dom: Domain, vbc, v, p=None, prm: PhiCgParams = None):
 def plume_step(dom: Domain, vbc, sbc, v, s, p, inflow, dt, inflow_rate, buoyancy, prm: PhiCgParams, mac_cormack=False):
     """incompressible_step: the fused notebook step (examples/grids/Smoke_Plume.ipynb:58-68); state updated in place."""
     require_cuda()
+    assert dom.halo == 0, "plume_step is the single-GPU fused call; z-slab runs sequence the step in phiflow_b200.dist"
     ws, res = dom.workspace()
     sp = PhiPlumeParams()
     sp.dt, sp.inflow_rate, sp.mac_cormack = dt, inflow_rate, int(mac_cormack)

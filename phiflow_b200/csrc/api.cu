@@ -34,13 +34,15 @@ int phi_make_dgrid(const PhiGrid* g, DGrid* o)
     if (!g) { phi_set_error("grid is NULL"); return PHI_ERR_INVALID; }
     if (g->dim != 2 && g->dim != 3) { phi_set_error("grid.dim must be 2 or 3, got %d", g->dim); return PHI_ERR_INVALID; }
     if (g->batch < 1) { phi_set_error("grid.batch must be >= 1"); return PHI_ERR_INVALID; }
-    o->dim = g->dim; o->batch = g->batch;
+    if (g->halo < 0 || (g->halo > 0 && g->dim != 3)) { phi_set_error("grid.halo must be 0 for 2-D grids"); return PHI_ERR_INVALID; }
+    o->dim = g->dim; o->batch = g->batch; o->halo = g->halo;
     for (int a = 0; a < 3; ++a) {
         const bool used = a < g->dim;
         o->n[a] = used ? g->n[a] : 1;
         o->cext[a] = used ? g->cext[a] : 1;
         o->fext[a] = used ? g->fext[a] : 1;
-        if (used && (g->n[a] < 1 || g->cext[a] < g->n[a] || g->fext[a] < g->n[a])) {
+        const int pad = (a == 2 && g->dim == 3) ? 2 * g->halo : 0;
+        if (used && (g->n[a] < 1 || g->cext[a] < g->n[a] + pad || g->fext[a] < g->n[a] + pad)) {
             phi_set_error("grid: n[%d]=%d cext=%d fext=%d invalid", a, g->n[a], g->cext[a], g->fext[a]); return PHI_ERR_INVALID;
         }
         if (used && !(g->dx[a] > 0.f)) { phi_set_error("grid: dx[%d] must be positive", a); return PHI_ERR_INVALID; }
@@ -64,7 +66,8 @@ static int check_bc(const PhiBC* bc, int dim)
 {
     if (!bc) { phi_set_error("boundary is NULL"); return PHI_ERR_INVALID; }
     for (int a = 0; a < dim; ++a) {
-        if (bc->lo[a] > 2 || bc->hi[a] > 2) { phi_set_error("boundary kind out of range on axis %d", a); return PHI_ERR_INVALID; }
+        if (bc->lo[a] > 3 || bc->hi[a] > 3) { phi_set_error("boundary kind out of range on axis %d", a); return PHI_ERR_INVALID; }
+        if ((bc->lo[a] == PHI_BC_HALO || bc->hi[a] == PHI_BC_HALO) && !(dim == 3 && a == 2)) { phi_set_error("PHI_BC_HALO is only valid on the z axis of 3-D grids"); return PHI_ERR_INVALID; }
         if ((bc->lo[a] == PHI_BC_PERIODIC) != (bc->hi[a] == PHI_BC_PERIODIC)) { phi_set_error("axis %d: PERIODIC must be set on both sides", a); return PHI_ERR_INVALID; }
     }
     return 0;
@@ -80,6 +83,8 @@ int phi_make_centered(const PhiGrid* g, const PhiBC* bc, DField* o)
         o->clo[a] = used ? bc->clo[a] : 0.f; o->chi[a] = used ? bc->chi[a] : 0.f;
     }
     set_strides(o, g->cext, g->dim);
+    o->halo = g->halo;
+    if ((bc->lo[g->dim - 1] == PHI_BC_HALO || bc->hi[g->dim - 1] == PHI_BC_HALO) && g->halo < 1) { phi_set_error("PHI_BC_HALO needs grid.halo >= 1"); return PHI_ERR_INVALID; }
     return 0;
 }
 
@@ -104,8 +109,8 @@ int phi_pressure_bc(const PhiVBC* vbc, int dim, PhiBC* o)
     memset(o, 0, sizeof(*o));
     for (int a = 0; a < dim; ++a) {
         const uint8_t kl = vbc->comp[a].lo[a], kh = vbc->comp[a].hi[a];
-        o->lo[a] = kl == PHI_BC_PERIODIC ? PHI_BC_PERIODIC : (kl == PHI_BC_ZERO_GRADIENT ? PHI_BC_CONST : PHI_BC_ZERO_GRADIENT);
-        o->hi[a] = kh == PHI_BC_PERIODIC ? PHI_BC_PERIODIC : (kh == PHI_BC_ZERO_GRADIENT ? PHI_BC_CONST : PHI_BC_ZERO_GRADIENT);
+        o->lo[a] = (kl == PHI_BC_PERIODIC || kl == PHI_BC_HALO) ? kl : (kl == PHI_BC_ZERO_GRADIENT ? PHI_BC_CONST : PHI_BC_ZERO_GRADIENT);
+        o->hi[a] = (kh == PHI_BC_PERIODIC || kh == PHI_BC_HALO) ? kh : (kh == PHI_BC_ZERO_GRADIENT ? PHI_BC_CONST : PHI_BC_ZERO_GRADIENT);
     }
     return 0;
 }

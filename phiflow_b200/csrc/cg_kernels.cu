@@ -307,7 +307,7 @@ int phi_launch_cg(const CgLaunch& l, cudaStream_t s)
     if (g.batch > CG_MAX_BATCH) { phi_set_error("cg: batch %d exceeds %d (split the batch)", g.batch, CG_MAX_BATCH); return PHI_ERR_UNSUPPORTED; }
     if (l.workspace_bytes < phi_cg_workspace_bytes(g)) { phi_set_error("cg: workspace %zu < %zu bytes", l.workspace_bytes, phi_cg_workspace_bytes(g)); return PHI_ERR_WORKSPACE; }
     if (phi_ring_enabled()) {
-        const int e = phi_launch_cg_ring(l, s);
+        const int e = phi_launch_cg_ring(l, nullptr, s);
         if (e != -100) return e;
     }
     int per_sm = 0;
@@ -322,6 +322,7 @@ int phi_launch_cg(const CgLaunch& l, cudaStream_t s)
     const size_t arr = align_up((size_t)pf_sb * g.batch * sizeof(float), 256);
     unsigned char* ws = (unsigned char*)l.workspace;
     a.rhs = l.rhs; a.x = l.x;
+    if (g.halo != 0) { phi_set_error("cg: z-slab grids need the TMA ring kernel (grid lines too long)"); return PHI_ERR_UNSUPPORTED; }
     a.r = (float*)ws; a.d0 = (float*)(ws + arr); a.d1 = (float*)(ws + 2 * arr);
     a.partials = (double*)(ws + 3 * arr);
     a.result = l.result; a.prm = l.prm;

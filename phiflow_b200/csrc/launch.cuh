@@ -24,6 +24,16 @@ struct CgLaunch {
 size_t phi_cg_workspace_bytes(const DGrid& g);
 // TMA ring fast paths (ring_kernels.cu); return -100 when the shape does not fit and the caller must fall back
 int phi_launch_laplace_ring(const DGrid& g, const DField& f, const float* x, float* y, float coeff, bool axpy, cudaStream_t s);
-int phi_launch_cg_ring(const CgLaunch& a, cudaStream_t s);
+#define PHI_MAX_RANKS 8
+struct CommDev {                      // device view of the multi-GPU communicator (comm.cu)
+    int rank, n;
+    int lower, upper;                 // z neighbours (-1: physical boundary)
+    double* mbox[PHI_MAX_RANKS];      // mailbox of every rank ([rank] = local), [2 parity][PHI_MAX_RANKS][2*CG_MAX_BATCH]
+    unsigned long long* flag[PHI_MAX_RANKS];   // [2 parity][PHI_MAX_RANKS] event numbers
+    unsigned long long* seq;          // local persistent event counter
+    float *lo_r, *lo_d0, *lo_d1;      // lower neighbour's CG vectors (first owned plane)
+    float *hi_r, *hi_d0, *hi_d1;      // upper neighbour's
+};
+int phi_launch_cg_ring(const CgLaunch& a, const CommDev* cm, cudaStream_t s);
 bool phi_ring_enabled();
 int phi_launch_cg(const CgLaunch& a, cudaStream_t s);

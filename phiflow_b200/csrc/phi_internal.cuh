@@ -14,6 +14,7 @@ struct DGrid {
     int dim, batch;
     int n[3];
     int cext[3], fext[3];          // allocated extents of centred arrays / staggered components
+    int halo;                      // z-slab halo planes on each side of the owned range (0 on one GPU)
     float dx[3], inv_dx[3], inv_dx2[3];
 };
 
@@ -25,6 +26,7 @@ struct DField {
     unsigned char klo[3], khi[3];
     float clo[3], chi[3];
     long long sy, sz, sb;          // strides (elements) of y, z, batch of this array
+    int halo;                      // planes readable beyond [lo, hi] on the last axis (PHI_BC_HALO)
 };
 
 struct DVec {                      // a staggered vector field
@@ -44,12 +46,14 @@ __device__ __forceinline__ bool phi_resolve(int& i, const DField& f, int a, floa
     const int lo = f.lo[a], hi = f.hi[a];
     if (i < lo) {
         const int k = f.klo[a];
+        if (k == PHI_BC_HALO) { i = max(i, lo - f.halo); return true; }
         if (k == PHI_BC_PERIODIC) { const int per = hi - lo + 1; int r = (i - lo) % per; if (r < 0) r += per; i = lo + r; return true; }
         if (k == PHI_BC_ZERO_GRADIENT) { i = lo; return true; }
         cval = f.clo[a]; return false;
     }
     if (i > hi) {
         const int k = f.khi[a];
+        if (k == PHI_BC_HALO) { i = min(i, hi + f.halo); return true; }
         if (k == PHI_BC_PERIODIC) { const int per = hi - lo + 1; i = lo + (i - lo) % per; return true; }
         if (k == PHI_BC_ZERO_GRADIENT) { i = hi; return true; }
         cval = f.chi[a]; return false;

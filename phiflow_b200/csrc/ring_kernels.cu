@@ -17,6 +17,7 @@
 // the common case runs a branch-free path: 5 LDS.128 + 2 SHFL + ~40 FP32 ops + 1 STG.128 per group.
 #include <cooperative_groups.h>
 #include "cg_common.cuh"
+#include <cstring>
 #include "launch.cuh"
 
 namespace cg = cooperative_groups;
@@ -433,6 +434,7 @@ __device__ __forceinline__ void ring_process_unit(Ring& rg, const RingCfg& cfg, 
             const int z = u.z0 + zi;
             const bool fast = tile_fast && !(z == 0 && pf.klo[2] == PHI_BC_CONST) && !(z == g.n[2] - 1 && pf.khi[2] == PHI_BC_CONST);
             ring_wait_full(rg, c2);
+            epi.set_plane(z, g.n[2]);
             ring_compute_any<GENERIC, DIM, NH, NE>(cfg, g, pf, tg, fast, ring_ptr(rg, cfg, a), ring_ptr(rg, cfg, bq), ring_ptr(rg, cfg, c2),
                                           beta, plane_off, z, epi);
             ring_release(rg, a);
@@ -445,6 +447,7 @@ __device__ __forceinline__ void ring_process_unit(Ring& rg, const RingCfg& cfg, 
         const SlotIt a = rg.pos;
         ring_wait_full(rg, a);
         const float* sc = ring_ptr(rg, cfg, a);
+        epi.set_plane(-1, 0);
         ring_compute_any<GENERIC, DIM, NH, NE>(cfg, g, pf, tg, tile_fast, sc, sc, sc, beta, plane_off, 0, epi);
         ring_release(rg, a);
         rg.pos.next(cfg.R);
@@ -452,9 +455,28 @@ __device__ __forceinline__ void ring_process_unit(Ring& rg, const RingCfg& cfg, 
 }
 
 // ---- epilogues (values of element-wise arrays arrive from shared memory) -------------------------------------------------
+// Multi-GPU: an epilogue that updates a vector whose halo the neighbouring slab needs also stores the first / last owned
+// plane into that neighbour's halo plane through a peer pointer (NVLink).  plo / phi are pre-offset so that the same
+// element offset `off` addresses the right halo plane; zf says whether the current plane is the first (1) / last (2).
+struct PeerHalo {
+    float* plo; float* phi; int zf;
+    __device__ __forceinline__ void set_plane(int z, int nz) { zf = ((z == 0 && plo) ? 1 : 0) | ((z == nz - 1 && phi) ? 2 : 0); }
+    __device__ __forceinline__ void put4(long long off, const float4& v) const
+    {
+        if (zf & 1) *reinterpret_cast<float4*>(plo + off) = v;
+        if (zf & 2) *reinterpret_cast<float4*>(phi + off) = v;
+    }
+    __device__ __forceinline__ void put1(long long off, float v) const
+    {
+        if (zf & 1) plo[off] = v;
+        if (zf & 2) phi[off] = v;
+    }
+};
+
 template <bool AXPY>
 struct REpiLaplace {
     float* y; float coeff;
+    __device__ __forceinline__ void set_plane(int, int) {}
     __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid, const float4&, const float4&)
     {
         float4 o = q;
@@ -465,33 +487,38 @@ struct REpiLaplace {
 };
 
 struct REpiResidual0 {          // e0 = rhs
-    float* r; float mean, offs; float acc0, acc1;
+    float* r; float mean, offs; float acc0, acc1; PeerHalo ph;
+    __device__ __forceinline__ void set_plane(int z, int nz) { ph.set_plane(z, nz); }
     __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid, const float4& y, const float4&)
     {
         float4 rt = make_float4((y.x - mean) - q.x, (y.y - mean) - q.y, (y.z - mean) - q.z, (y.w - mean) - q.w);
         float4 rr = make_float4(rt.x - offs, rt.y - offs, rt.z - offs, rt.w - offs);
         if (nvalid == 4) {
             *reinterpret_cast<float4*>(r + off) = rr;
+            if (ph.zf) ph.put4(off, rr);
             acc0 += rr.x * rr.x + rr.y * rr.y + rr.z * rr.z + rr.w * rr.w;
             acc1 += rt.x * rt.x + rt.y * rt.y + rt.z * rt.z + rt.w * rt.w;
-        } else for (int j = 0; j < nvalid; ++j) { const float a = f4_get(rr, j), t = f4_get(rt, j); r[off + j] = a; acc0 += a * a; acc1 += t * t; }
+        } else for (int j = 0; j < nvalid; ++j) { const float a = f4_get(rr, j), t = f4_get(rt, j); r[off + j] = a; if (ph.zf) ph.put1(off + j, a); acc0 += a * a; acc1 += t * t; }
     }
 };
 
 struct REpiPassA {
-    float* dnew; float acc0, acc1;
+    float* dnew; float acc0, acc1; PeerHalo ph;
+    __device__ __forceinline__ void set_plane(int z, int nz) { ph.set_plane(z, nz); }
     __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid, const float4&, const float4&)
     {
         if (nvalid == 4) {
             *reinterpret_cast<float4*>(dnew + off) = c;
+            if (ph.zf) ph.put4(off, c);
             acc0 += c.x * q.x + c.y * q.y + c.z * q.z + c.w * q.w;
             acc1 += (c.x + c.y) + (c.z + c.w);
-        } else for (int j = 0; j < nvalid; ++j) { const float v = f4_get(c, j); dnew[off + j] = v; acc0 += v * f4_get(q, j); acc1 += v; }
+        } else for (int j = 0; j < nvalid; ++j) { const float v = f4_get(c, j); dnew[off + j] = v; if (ph.zf) ph.put1(off + j, v); acc0 += v * f4_get(q, j); acc1 += v; }
     }
 };
 
 struct REpiPassB {              // e0 = x, e1 = r
-    float* x; float* r; float alpha, offs; float acc0, acc1;
+    float* x; float* r; float alpha, offs; float acc0, acc1; PeerHalo ph;
+    __device__ __forceinline__ void set_plane(int z, int nz) { ph.set_plane(z, nz); }
     __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid, const float4& xe, const float4& re)
     {
         float4 xv = xe, rv = re;
@@ -500,8 +527,9 @@ struct REpiPassB {              // e0 = x, e1 = r
         if (nvalid == 4) {
             *reinterpret_cast<float4*>(x + off) = xv;
             *reinterpret_cast<float4*>(r + off) = rv;
+            if (ph.zf) ph.put4(off, rv);
             acc0 += rv.x * rv.x + rv.y * rv.y + rv.z * rv.z + rv.w * rv.w;
-        } else for (int j = 0; j < nvalid; ++j) { x[off + j] = f4_get(xv, j); const float t = f4_get(rv, j); r[off + j] = t; acc0 += t * t; }
+        } else for (int j = 0; j < nvalid; ++j) { x[off + j] = f4_get(xv, j); const float t = f4_get(rv, j); r[off + j] = t; if (ph.zf) ph.put1(off + j, t); acc0 += t * t; }
     }
 };
 
@@ -529,7 +557,58 @@ struct CgRingArgs {
     CgArgs a;
     RingCfg cfg;
     int ring_smem_offset;        // byte offset of the ring inside dynamic shared memory (after the CgShared block)
+    CommDev cm;
 };
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// All-reduce of the two per-batch sums across the ranks, executed inside the persistent kernel after the local
+// reduction: block 0 writes this rank's sums into every rank's mailbox (NVLink peer stores) and raises a flag; every CTA
+// of every rank waits for the n flags in its OWN mailbox and adds the n entries in rank order (bitwise identical
+// everywhere).  Event `seq` uses mailbox half seq&1; a rank can be at most one event ahead of the slowest one.
+__device__ __forceinline__ bool comm_allreduce(const CommDev& cm, const CgShared& sh, int batch, unsigned long long seq)
+{
+    const int par = (int)(seq & 1ull);
+    const size_t stride = 2 * (size_t)CG_MAX_BATCH;
+    if (blockIdx.x == 0) {
+        for (int q = 0; q < cm.n; ++q) {
+            double* dst = cm.mbox[q] + ((size_t)par * PHI_MAX_RANKS + cm.rank) * stride;
+            for (int b = threadIdx.x; b < batch; b += blockDim.x) { dst[b] = sh.sum0[b]; dst[CG_MAX_BATCH + b] = sh.sum1[b]; }
+        }
+        __threadfence_system();
+        __syncthreads();
+        if ((int)threadIdx.x < cm.n) st_release_sys(cm.flag[threadIdx.x] + par * PHI_MAX_RANKS + cm.rank, seq);
+    }
+    bool ok = true;
+    if ((int)threadIdx.x < cm.n) {
+        const unsigned long long* f = cm.flag[cm.rank] + par * PHI_MAX_RANKS + threadIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < seq) {
+            if (clock64() - t0 > 40000000000ll) { ok = false; break; }        // ~20 s: a peer died; do not hang the GPU
+        }
+    }
+    ok = __syncthreads_and(ok);
+    const double* src = cm.mbox[cm.rank] + (size_t)par * PHI_MAX_RANKS * stride;
+    for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+        double s0 = 0, s1 = 0;
+        for (int q = 0; q < cm.n; ++q) {
+            s0 += *(volatile const double*)(src + q * stride + b);
+            s1 += *(volatile const double*)(src + q * stride + CG_MAX_BATCH + b);
+        }
+        sh.sum0[b] = s0; sh.sum1[b] = s1;
+    }
+    __syncthreads();
+    return ok;
+}
 
 template <int DIM, class F>
 __device__ __forceinline__ void ring_unit_cells(const RingCfg& cfg, const DGrid& g, const DField& pf, const ThreadGroups& tg,
@@ -560,7 +639,7 @@ k_cg_ring(CgRingArgs A)
     cg::grid_group grid = cg::this_grid();
     const DGrid& g = a.g;
     const int batch = g.batch;
-    const double cells = (double)g.n[0] * g.n[1] * g.n[2];
+    const double cells = (double)g.n[0] * g.n[1] * g.n[2] * (A.cm.n > 1 ? A.cm.n : 1);   // global cell count (equal slabs)
     const float coffs = a.prm.matrix_offset;
     int region = 0;
     ThreadGroups tg;
@@ -579,12 +658,28 @@ k_cg_ring(CgRingArgs A)
         }
         if (cur_b >= 0) flush_partials(sh, a.partials, region, batch, cur_b, acc0, acc1);
     };
+    const CommDev& cm = A.cm;
+    unsigned long long seq = cm.n > 1 ? *cm.seq : 0ull;
+    bool comm_ok = true;
     auto barrier_and_reduce = [&](const unsigned char* active) {
         fence_proxy_async();                       // generic-proxy stores of this pass -> later TMA (async proxy) loads
+        if (cm.n > 1) __threadfence_system();      // halo planes stored into the neighbours' memory
         grid.sync();
         fence_proxy_async();
         reduce_partials(sh, a.partials, region, batch, cfg.units_per_batch, active);
         region ^= 1;
+        if (cm.n > 1) {
+            comm_ok = comm_allreduce(cm, sh, batch, ++seq) && comm_ok;
+            fence_proxy_async();
+        }
+    };
+    const long long nzsz = (long long)g.n[2] * a.pf.sz;
+    auto peer_halo = [&](float* lo_arr, float* hi_arr) {
+        PeerHalo ph;
+        ph.plo = (cm.n > 1 && cm.lower >= 0) ? lo_arr + nzsz : nullptr;
+        ph.phi = (cm.n > 1 && cm.upper >= 0) ? hi_arr - nzsz : nullptr;
+        ph.zf = 0;
+        return ph;
     };
 
     for (int b = threadIdx.x; b < batch; b += blockDim.x) { sh.mean[b] = 0.f; sh.offs[b] = 0.f; }
@@ -608,7 +703,7 @@ k_cg_ring(CgRingArgs A)
         const float* hsrc[2] = {a.x, nullptr};
         const float* esrc[2] = {a.rhs, nullptr};
         sweep(nullptr, [&](const RingUnit& u, float& acc0, float& acc1) {
-            REpiResidual0 epi{a.r, sh.mean[u.b], sh.offs[u.b], 0.f, 0.f};
+            REpiResidual0 epi{a.r, sh.mean[u.b], sh.offs[u.b], 0.f, 0.f, peer_halo(cm.lo_r, cm.hi_r)};
             ring_process_unit<GENERIC, DIM, 1, 1>(rg, cfg, g, a.pf, tg, hsrc, esrc, 0.f, u, epi);
             acc0 += epi.acc0; acc1 += epi.acc1;
         });
@@ -630,12 +725,13 @@ k_cg_ring(CgRingArgs A)
     __syncthreads();
 
     float* dold = a.d0; float* dnew = a.d1;
-    while (*sh.any_cont) {
+    float* lo_dnew = cm.lo_d1; float* hi_dnew = cm.hi_d1; float* lo_dold = cm.lo_d0; float* hi_dold = cm.hi_d0;
+    while (*sh.any_cont && comm_ok) {
         {   // pass A
             const float* hsrc[2] = {a.r, dold};
             const float* esrc[2] = {nullptr, nullptr};
             sweep(sh.cont, [&](const RingUnit& u, float& acc0, float& acc1) {
-                REpiPassA epi{dnew, 0.f, 0.f};
+                REpiPassA epi{dnew, 0.f, 0.f, peer_halo(lo_dnew, hi_dnew)};
                 ring_process_unit<GENERIC, DIM, 2, 0>(rg, cfg, g, a.pf, tg, hsrc, esrc, sh.beta[u.b], u, epi);
                 acc0 += epi.acc0; acc1 += epi.acc1;
             });
@@ -653,7 +749,7 @@ k_cg_ring(CgRingArgs A)
             const float* hsrc[2] = {dnew, nullptr};
             const float* esrc[2] = {a.x, a.r};
             sweep(sh.cont, [&](const RingUnit& u, float& acc0, float& acc1) {
-                REpiPassB epi{a.x, a.r, sh.alpha[u.b], sh.offs[u.b], 0.f, 0.f};
+                REpiPassB epi{a.x, a.r, sh.alpha[u.b], sh.offs[u.b], 0.f, 0.f, peer_halo(cm.lo_r, cm.hi_r)};
                 ring_process_unit<GENERIC, DIM, 1, 2>(rg, cfg, g, a.pf, tg, hsrc, esrc, 0.f, u, epi);
                 acc0 += epi.acc0;
             });
@@ -676,6 +772,8 @@ k_cg_ring(CgRingArgs A)
         if (threadIdx.x == 0) { int any = 0; for (int b = 0; b < batch; ++b) any |= sh.cont[b]; *sh.any_cont = any; }
         __syncthreads();
         float* t = dold; dold = dnew; dnew = t;
+        t = lo_dold; lo_dold = lo_dnew; lo_dnew = t;
+        t = hi_dold; hi_dold = hi_dnew; hi_dnew = t;
     }
 
     if (a.prm.project_mean) {
@@ -694,10 +792,11 @@ k_cg_ring(CgRingArgs A)
         }
     }
 
+    if (cm.n > 1 && blockIdx.x == 0 && threadIdx.x == 0) *cm.seq = seq;
     if (blockIdx.x == 0) {
         for (int b = threadIdx.x; b < batch; b += blockDim.x) {
             PhiCgResult res;
-            res.iterations = sh.iters[b]; res.converged = sh.conv[b]; res.diverged = sh.divg[b];
+            res.iterations = sh.iters[b]; res.converged = sh.conv[b]; res.diverged = comm_ok ? sh.divg[b] : -1;
             res.residual_sq = fabsf((float)sh.delta[b]); res.tol_sq = sh.tol_sq[b]; res.initial_residual_sq = sh.rsq0[b];
             a.result[b] = res;
         }
@@ -784,7 +883,7 @@ int phi_launch_laplace_ring(const DGrid& g, const DField& f, const float* x, flo
     return (int)cudaGetLastError();
 }
 
-int phi_launch_cg_ring(const CgLaunch& l, cudaStream_t s)
+int phi_launch_cg_ring(const CgLaunch& l, const CommDev* cm, cudaStream_t s)
 {
     const DGrid& g = l.g;
     if (g.batch > CG_MAX_BATCH) return -100;
@@ -811,9 +910,11 @@ int phi_launch_cg_ring(const CgLaunch& l, cudaStream_t s)
     CgArgs& a = A.a;
     a.g = g; a.pf = l.pf; a.um = UnitMap();
     a.rhs = l.rhs; a.x = l.x;
-    a.r = (float*)ws; a.d0 = (float*)(ws + arr); a.d1 = (float*)(ws + 2 * arr);
+    const size_t hoff = (size_t)g.halo * g.cext[0] * g.cext[1];       // pointers address the first owned plane
+    a.r = (float*)ws + hoff; a.d0 = (float*)(ws + arr) + hoff; a.d1 = (float*)(ws + 2 * arr) + hoff;
     a.partials = (double*)(ws + 3 * arr);
     a.result = l.result; a.prm = l.prm;
+    if (cm) A.cm = *cm; else { memset(&A.cm, 0, sizeof(A.cm)); A.cm.n = 1; A.cm.lower = A.cm.upper = -1; }
     void* args[] = {&A};
     e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(RING_THREADS), args, smem, s);
     if (e != cudaSuccess) { phi_set_error("cg ring: cooperative launch failed: %s", cudaGetErrorString(e)); return (int)e; }

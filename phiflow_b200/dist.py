@@ -1,0 +1,178 @@
+"""
+Multi-GPU execution of the hot path: one process per GPU, z-slab decomposition.
+
+Rank r owns planes [r*nz/P, (r+1)*nz/P) of every array plus `halo` planes on each side.  Interior slab faces get the
+boundary kind 'halo' (PHI_BC_HALO): kernels read neighbour values from the halo planes, which this module keeps current
+with grouped send/recv over torch.distributed (NCCL on GPUs, gloo in the CPU tests of the host logic).
+The pressure solve itself needs no host-side communication: phicuda_cg_poisson_dist_f32 runs the whole CG in one
+persistent kernel per rank that exchanges halo planes and dot products through NVLink peer memory (csrc/comm.cu).
+Batched 2-D runs shard the batch axis instead - entries are independent systems, no communication at all.
+"""
+import ctypes as C
+from typing import List, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, _ops as ops
+
+HALO, PERIODIC = 'halo', 'periodic'
+
+
+def local_bc(spec, rank: int, world: int):
+    """Boundary spec of a slab: z sides that border another rank become 'halo'."""
+    if world == 1:
+        return spec
+    if isinstance(spec, list):
+        return [local_bc(s, rank, world) for s in spec]
+    lo, hi = spec[2]
+    periodic = lo == PERIODIC
+    zlo = HALO if (periodic or rank > 0) else lo
+    zhi = HALO if (periodic or rank < world - 1) else hi
+    return (spec[0], spec[1], (zlo, zhi))
+
+
+class Slab:
+    """Geometry + communication of one rank's z-slab."""
+
+    def __init__(self, global_res: Sequence[int], dx: Sequence[float], vbc, halo: int = 2, device='cuda', group=None):
+        assert len(global_res) == 3, "z-slab decomposition is for 3-D grids"
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        nx, ny, nz = global_res
+        assert nz % self.world == 0, f"nz={nz} must be divisible by the number of ranks {self.world}"
+        self.global_res = tuple(global_res)
+        self.nz = nz // self.world
+        self.z0 = self.rank * self.nz
+        self.halo = halo if self.world > 1 else 0
+        assert self.halo <= self.nz, "halo wider than the slab"
+        self.vbc_global = vbc
+        self.vbc = local_bc(vbc, self.rank, self.world)
+        spec = vbc[0] if isinstance(vbc, list) else vbc
+        periodic = spec[2][0] == PERIODIC
+        self.lower = None if self.world == 1 else ((self.rank - 1) % self.world if (periodic or self.rank > 0) else None)
+        self.upper = None if self.world == 1 else ((self.rank + 1) % self.world if (periodic or self.rank < self.world - 1) else None)
+        self.dom = ops.Domain((nx, ny, self.nz), dx, 1, vbc=self.vbc, device=device, halo=self.halo)
+        self._comm = None
+
+    def bc(self, spec):
+        return local_bc(spec, self.rank, self.world)
+
+    # ---- halo exchange --------------------------------------------------------------------------------------------
+    def exchange(self, tensors: List[torch.Tensor], width: int):
+        """Fills `width` halo planes on both sides of every tensor from the neighbouring slabs."""
+        if self.world == 1:
+            return
+        H, nz = self.halo, self.nz
+        assert 1 <= width <= H
+        ops_ = []
+        recv_views = []
+        for t in tensors:
+            # order matters when lower == upper (two ranks, periodic): sends and receives pair up in issue order
+            if self.upper is not None:
+                ops_.append(dist.P2POp(dist.isend, t[:, H + nz - width:H + nz].contiguous(), self.upper, self.group))
+            if self.lower is not None:
+                ops_.append(dist.P2POp(dist.isend, t[:, H:H + width].contiguous(), self.lower, self.group))
+        for t in tensors:
+            if self.lower is not None:
+                buf = torch.empty_like(t[:, H - width:H])
+                ops_.append(dist.P2POp(dist.irecv, buf, self.lower, self.group))
+                recv_views.append((t[:, H - width:H], buf))
+            if self.upper is not None:
+                buf = torch.empty_like(t[:, H + nz:H + nz + width])
+                ops_.append(dist.P2POp(dist.irecv, buf, self.upper, self.group))
+                recv_views.append((t[:, H + nz:H + nz + width], buf))
+        for req in dist.batch_isend_irecv(ops_):
+            req.wait()
+        for view, buf in recv_views:
+            view.copy_(buf)
+
+    # ---- distributed pressure solve -----------------------------------------------------------------------------------
+    def _communicator(self):
+        if self._comm is None:
+            lib = _lib.load()
+            handle = (C.c_ubyte * 64)()
+            comm = C.c_void_p()
+            _lib.check(lib.phicuda_comm_create(self.rank, self.world, C.byref(self.dom.grid), C.byref(comm), handle))
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.dom.device)
+            gathered = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(gathered, mine, group=self.group)
+            allh = (C.c_ubyte * (64 * self.world))(*torch.cat(gathered).cpu().tolist())
+            _lib.check(lib.phicuda_comm_connect(comm, allh))
+            dist.barrier(group=self.group)
+            self._comm = comm
+            self._result = torch.zeros(6, dtype=torch.int32, device=self.dom.device)
+        return self._comm
+
+    def cg_poisson(self, rhs: torch.Tensor, x: torch.Tensor, prm):
+        """CG over all slabs; x (with valid halo planes) is updated in place.  Single rank: the ordinary solve."""
+        if self.world == 1:
+            return ops.cg_poisson(self.dom, self.vbc, rhs, x, prm)
+        comm = self._communicator()
+        dom = self.dom
+        _lib.check(_lib.load().phicuda_cg_poisson_dist_f32(C.byref(dom.grid), C.byref(ops.make_vbc(self.vbc, 3)), ops._ptr(rhs, dom.coff),
+                                                           ops._ptr(x, dom.coff), C.byref(prm), ops._ptr(self._result), comm, ops._stream()))
+        return x
+
+    def results(self):
+        if self.world == 1:
+            return ops.read_results(self.dom)
+        return self._result.cpu().numpy().view(ops._RESULT_DTYPE)
+
+    def result_tensor(self):
+        return self.dom.workspace()[1] if self.world == 1 else self._result
+
+    def close(self):
+        if self._comm is not None:
+            _lib.load().phicuda_comm_destroy(self._comm)
+            self._comm = None
+
+
+class SlabPlume:
+    """incompressible_step on z-slabs.  State lives on the device of each rank."""
+
+    def __init__(self, slab: Slab, sbc, dt, inflow_rate, buoyancy, prm, adv_halo=None):
+        self.slab, self.dom = slab, slab.dom
+        self.vbc, self.sbc = slab.vbc, slab.bc(sbc)
+        self.dt, self.inflow_rate, self.buoyancy, self.prm = dt, inflow_rate, buoyancy, prm
+        self.adv_halo = adv_halo if adv_halo is not None else slab.halo
+        d = self.dom
+        self.v, self.v2 = d.alloc_faces(), d.alloc_faces()
+        self.s, self.s2 = d.alloc_centered(), d.alloc_centered()
+        self.p, self.div = d.alloc_centered(), d.alloc_centered()
+        self.inflow = d.alloc_centered()
+        self.launches_per_step = 9
+
+    def project(self):
+        s = self.slab
+        s.exchange(self.v, 1)
+        ops.divergence(self.dom, self.vbc, self.v, out=self.div)
+        s.exchange([self.p], 1)
+        s.cg_poisson(self.div, self.p, self.prm)
+        s.exchange([self.p], 1)
+        ops.grad_sub(self.dom, self.vbc, self.v, self.p)
+
+    def step(self, cg_events=None):
+        s, d = self.slab, self.dom
+        if s.world > 1:
+            s.exchange(self.v + [self.s], self.adv_halo)
+        ops.advect_centered(d, self.vbc, self.v, self.sbc, self.s, self.dt, out=self.s2)
+        ops.axpy_centered(d, self.inflow_rate, self.inflow, self.s2)
+        ops.advect_staggered(d, self.vbc, self.v, self.vbc, self.v, self.dt, out=self.v2)
+        s.exchange([self.s2], 1)
+        ops.add_buoyancy(d, self.vbc, self.sbc, self.s2, self.buoyancy, self.dt, self.v2)
+        self.s, self.s2 = self.s2, self.s
+        self.v, self.v2 = self.v2, self.v
+        s.exchange(self.v, 1)
+        ops.divergence(d, self.vbc, self.v, out=self.div)
+        s.exchange([self.p], 1)
+        if cg_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        s.cg_poisson(self.div, self.p, self.prm)
+        if cg_events is not None:
+            e1.record()
+            cg_events.append((e0, e1))
+        s.exchange([self.p], 1)
+        ops.grad_sub(d, self.vbc, self.v, self.p)

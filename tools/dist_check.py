@@ -1,0 +1,107 @@
+#!/usr/bin/env python
+"""
+Multi-GPU parity check:  torchrun --nproc-per-node N tools/dist_check.py
+Every rank runs its z-slab of a small plume; rank 0 additionally runs the whole grid on its own GPU with the
+single-GPU kernels, and the gathered slab results must agree with it (the distributed solve only changes the order of
+the dot-product reductions).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from phiflow_b200 import _ops as ops  # noqa: E402
+from phiflow_b200.dist import Slab, SlabPlume  # noqa: E402
+
+
+def gather_centered(slab, t):
+    H, nz = slab.halo, slab.nz
+    own = t[:, H:H + nz].contiguous()
+    parts = [torch.empty_like(own) for _ in range(slab.world)]
+    dist.all_gather(parts, own)
+    return torch.cat(parts, dim=1)
+
+
+def run_case(name, vbc, sbc, res, steps, rtol):
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    dx = tuple(100.0 / r for r in res)
+    rng = np.random.default_rng(5)
+    nx, ny, nz = res
+    # global initial state in device layout (z, y, x); staggered arrays are filled on every index (unused slots are ignored)
+    v0 = [(0.05 * rng.standard_normal((1, nz + 1, ny + 1, nx + 4))).astype(np.float32) for _ in range(3)]
+    zc, yc, xc = np.meshgrid(np.arange(nz) + .5, np.arange(ny) + .5, np.arange(nx) + .5, indexing='ij')
+    inflow = np.clip(1.5 - np.sqrt((xc * dx[0] - 50) ** 2 + (yc * dx[1] - 50) ** 2 + (zc * dx[2] - 30) ** 2) / 10.0, 0, 1).astype(np.float32)[None]
+    prm = ops.cg_params(vbc, rtol=rtol, atol=1e-7, max_iter=2000)
+
+    slab = Slab(res, dx, vbc, halo=3, device=dev)
+    sim = SlabPlume(slab, sbc, 0.5, 0.2, (0.0, 0.0, 0.1), prm)
+    H, nzl, z0 = slab.halo, slab.nz, slab.z0
+    d = slab.dom
+    for c in range(3):
+        ez, ey, ex = d.fext[2] - 2 * H, d.fext[1], d.fext[0]
+        sim.v[c][:, H:H + ez] = torch.from_numpy(v0[c][:, z0:z0 + ez, :ey, :ex]).to(dev)
+    sim.inflow[:, H:H + nzl, :, :nx] = torch.from_numpy(inflow[:, z0:z0 + nzl]).to(dev)
+    sim.project()
+    iters = []
+    for _ in range(steps):
+        sim.step()
+        iters.append(int(slab.results()['iterations'][0]))
+    s_all = gather_centered(slab, sim.s)
+    p_all = gather_centered(slab, sim.p)
+    div = ops.divergence(d, slab.vbc, sim.v)          # needs v halo of the upper neighbour
+    slab.exchange(sim.v, 1)
+    div = ops.divergence(d, slab.vbc, sim.v)
+    div_all = gather_centered(slab, div)
+    ok = True
+    if rank == 0:
+        dom = ops.Domain(res, dx, 1, vbc=vbc, device=dev)
+        v = []
+        for c in range(3):
+            t = dom.alloc_faces()[0]
+            ez, ey, ex = dom.fext[2], dom.fext[1], dom.fext[0]
+            t[:] = torch.from_numpy(v0[c][:, :ez, :ey, :ex]).to(dev)
+            v.append(t)
+        s, p = dom.alloc_centered(), dom.alloc_centered()
+        infl = dom.alloc_centered()
+        infl[:, :, :, :nx] = torch.from_numpy(inflow).to(dev)
+        ops.make_incompressible(dom, vbc, v, p, prm)
+        ref_iters = []
+        for _ in range(steps):
+            ops.plume_step(dom, vbc, sbc, v, s, p, infl, 0.5, 0.2, (0.0, 0.0, 0.1), prm)
+            ref_iters.append(int(ops.read_results(dom)['iterations'][0]))
+        ds = float((s_all - s).abs().max()); sm = float(s.abs().max())
+        dp = float((p_all - p).abs().max()); pm = float(p.abs().max())
+        dmax = float(div_all.abs().max())
+        vmax = max(float(c.abs().max()) for c in v)
+        print(f"[{name}] world={world} iters dist={iters} single={ref_iters} | max|s diff|={ds:.3e} (max {sm:.3e}) "
+              f"max|p diff|={dp:.3e} (max {pm:.3e}) max|div|={dmax:.3e} vmax={vmax:.3e}", flush=True)
+        ok = ds <= 1e-3 * max(sm, 1e-3) and dp <= 50 * rtol * max(pm, 1e-6) and all(abs(a - b) <= max(3, b // 10) for a, b in zip(iters, ref_iters))
+        ok = ok and dmax <= 50 * rtol * vmax * sum(2.0 / h for h in dx)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    slab.close()
+    return bool(flag.item())
+
+
+def main():
+    dist.init_process_group('nccl')
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    world = dist.get_world_size()
+    per = (('periodic', 'periodic'),) * 3
+    mixed = (('periodic', 'periodic'), (0.0, 0.0), (0.0, 'zg'))
+    zg = (('zg', 'zg'),) * 3
+    ok = True
+    ok &= run_case('periodic', per, zg, (64, 48, 16 * world), 3, 1e-4)
+    ok &= run_case('mixed-z-wall-open', mixed, zg, (128, 24, 8 * world), 2, 1e-4)
+    if dist.get_rank() == 0:
+        print('DIST_CHECK', 'PASS' if ok else 'FAIL', flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == '__main__':
+    main()
