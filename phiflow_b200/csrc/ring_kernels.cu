@@ -423,7 +423,7 @@ __device__ __forceinline__ void ring_process_unit(Ring& rg, const RingCfg& cfg, 
     const int ny = g.n[1];
     const bool tile_fast = !GENERIC || tg.fast_ok && u.y0 + cfg.TY <= ny
                            && !(u.y0 == 0 && pf.klo[1] == PHI_BC_CONST) && !(u.y0 + cfg.TY == ny && pf.khi[1] == PHI_BC_CONST);
-    if (GENERIC && !tile_fast) groups_tile(tg, cfg, g, pf, u.y0);
+    if (GENERIC) groups_tile(tg, cfg, g, pf, u.y0);      // also needed on fast tiles: planes with constant z ghosts take the slow path
     long long plane_off = (long long)u.b * pf.sb + (long long)u.y0 * pf.sy + (DIM == 3 ? (long long)u.z0 * pf.sz : 0);
     if (DIM == 3) {
         const int nz = u.z1 - u.z0;

@@ -50,12 +50,20 @@ def run_case(name, vbc, sbc, res, steps, rtol):
     for _ in range(steps):
         sim.step()
         iters.append(int(slab.results()['iterations'][0]))
+        if rank == 0:
+            print(f"[{name}] dist solve result: {slab.results()}", flush=True)
     s_all = gather_centered(slab, sim.s)
     p_all = gather_centered(slab, sim.p)
     div = ops.divergence(d, slab.vbc, sim.v)          # needs v halo of the upper neighbour
     slab.exchange(sim.v, 1)
     div = ops.divergence(d, slab.vbc, sim.v)
     div_all = gather_centered(slab, div)
+    v_all = []
+    for c in range(3):
+        own = sim.v[c][:, H:H + nzl].contiguous()
+        parts = [torch.empty_like(own) for _ in range(world)]
+        dist.all_gather(parts, own)
+        v_all.append(torch.cat(parts, dim=1))
     ok = True
     if rank == 0:
         dom = ops.Domain(res, dx, 1, vbc=vbc, device=dev)
@@ -73,9 +81,14 @@ def run_case(name, vbc, sbc, res, steps, rtol):
         for _ in range(steps):
             ops.plume_step(dom, vbc, sbc, v, s, p, infl, 0.5, 0.2, (0.0, 0.0, 0.1), prm)
             ref_iters.append(int(ops.read_results(dom)['iterations'][0]))
+            print(f"[{name}] single solve result: {ops.read_results(dom)}", flush=True)
         ds = float((s_all - s).abs().max()); sm = float(s.abs().max())
         dp = float((p_all - p).abs().max()); pm = float(p.abs().max())
         dmax = float(div_all.abs().max())
+        ref_div = ops.divergence(dom, vbc, v)
+        loc = np.unravel_index(int(div_all.abs().argmax()), div_all.shape)
+        dv = [float((v_all[c][:, :nz, :dom.fext[1], :dom.fext[0]] - v[c][:, :nz]).abs().max()) for c in range(3)]
+        print(f"[{name}] ref max|div|={float(ref_div.abs().max()):.3e} dist-div argmax at (b,z,y,x)={loc} max|v diff| per comp={dv}", flush=True)
         vmax = max(float(c.abs().max()) for c in v)
         print(f"[{name}] world={world} iters dist={iters} single={ref_iters} | max|s diff|={ds:.3e} (max {sm:.3e}) "
               f"max|p diff|={dp:.3e} (max {pm:.3e}) max|div|={dmax:.3e} vmax={vmax:.3e}", flush=True)
