@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libphicuda.so')
+LIB_PATH = os.environ.get('PHICUDA_LIB', os.path.join(_HERE, 'lib', 'libphicuda.so'))   # override: diagnostics only
 
 BC_CONST, BC_ZERO_GRADIENT, BC_PERIODIC, BC_HALO = 0, 1, 2, 3
 ERR_INVALID, ERR_UNSUPPORTED, ERR_WORKSPACE = -1, -2, -3

@@ -115,23 +115,23 @@ k_advect(DGrid g, DVec vel, DField ff, int target, const float* __restrict__ src
     dst[(long long)b * ff.sb + (long long)z * ff.sz + (long long)y * ff.sy + x] = r;
 }
 
-// second MacCormack pass (advect.py:205-215): fwd = tmp (semi-Lagrangian result), bwd = sample(fwd, x + dt v),
-// new = fwd + strength*0.5*(field - bwd), clamped to the min/max of the 2^d neighbours of the backward lookup.
+// MacCormack (advect.py:182-215) = three passes over proven building blocks:
+//   fwd = semi_lagrangian(field, dt)            (k_advect)
+//   bwd = sample(fwd, x + dt v)                 (k_advect with -dt)
+//   new = fwd + strength*0.5*(field - bwd), clamped to the min/max of the 2^d neighbours of the backward lookup
 template <int DIM>
 __global__ void __launch_bounds__(128)
-k_mac_cormack2(DGrid g, DVec vel, DField ff, const float* __restrict__ src, const float* __restrict__ fwd,
-               float* __restrict__ dst, float dt, float half_strength)
+k_mac_cormack_combine(DGrid g, DVec vel, DField ff, const float* __restrict__ src, const float* __restrict__ fwd,
+                      float* bwd_dst, float dt, float half_strength)
 {
     int b, x, y, z;
     if (!advect_index<DIM>(g, ff, b, x, y, z)) return;
     const long long off = (long long)b * ff.sb + (long long)z * ff.sz + (long long)y * ff.sy + x;
-    const Lookup Lf = phi_lookup<DIM>(g, vel, -1, b, x, y, z, -dt);
-    const float bwd = phi_interp<DIM, false>(fwd, g, ff, b, Lf, nullptr, nullptr);
     const Lookup Lb = phi_lookup<DIM>(g, vel, -1, b, x, y, z, dt);
     float mn, mx;
     (void)phi_interp<DIM, true>(src, g, ff, b, Lb, &mn, &mx);
-    const float nv = fwd[off] + half_strength * (src[off] - bwd);
-    dst[off] = fminf(fmaxf(nv, mn), mx);
+    const float nv = fwd[off] + half_strength * (src[off] - bwd_dst[off]);
+    bwd_dst[off] = fminf(fmaxf(nv, mn), mx);
 }
 
 static dim3 scalar_grid(const DGrid& g)
@@ -152,8 +152,10 @@ int phi_launch_mac_cormack(const DGrid& g, const DVec& vel, const DField& ff, co
 {
     int err = phi_launch_advect(g, vel, ff, -1, src, tmp, dt, s);
     if (err) return err;
+    err = phi_launch_advect(g, vel, ff, -1, tmp, dst, -dt, s);
+    if (err) return err;
     const float hs = strength * 0.5f;
-    if (g.dim == 3) k_mac_cormack2<3><<<scalar_grid(g), 128, 0, s>>>(g, vel, ff, src, tmp, dst, dt, hs);
-    else            k_mac_cormack2<2><<<scalar_grid(g), 128, 0, s>>>(g, vel, ff, src, tmp, dst, dt, hs);
+    if (g.dim == 3) k_mac_cormack_combine<3><<<scalar_grid(g), 128, 0, s>>>(g, vel, ff, src, tmp, dst, dt, hs);
+    else            k_mac_cormack_combine<2><<<scalar_grid(g), 128, 0, s>>>(g, vel, ff, src, tmp, dst, dt, hs);
     return (int)cudaGetLastError();
 }
