@@ -13,6 +13,44 @@ DT, INFLOW_RATE, BUOYANCY = 0.5, 0.2, (0.0, 0.0, 0.1)
 RTOL, ATOL, MAX_ITER = 1e-3, 1e-5, 1000
 
 
+def run_e2e(sim, slab, args, dev):
+    """Per rank: the slab state (v, s, p) lives in pinned HOST arrays in the reference's (x, y, z) order; every step uploads
+    it, transposes to the device layout, steps (halo exchange + kernels), transposes back and downloads it."""
+    H, nz = slab.halo, slab.nz
+    names = ('vx', 'vy', 'vz', 's', 'p')
+    cur = {'vx': sim.v[0], 'vy': sim.v[1], 'vz': sim.v[2], 's': sim.s, 'p': sim.p}
+    host = {k: torch.zeros(tuple(reversed(cur[k][0, H:H + nz].shape)), dtype=torch.float32).pin_memory() for k in names}
+    for k in names:
+        host[k].copy_(cur[k][0, H:H + nz].permute(2, 1, 0))
+    torch.cuda.synchronize()
+    nbytes = sum(h.numel() * 4 for h in host.values()) * slab.world
+    steps = max(2, min(args.steps, 5))
+
+    def one():
+        cur = {'vx': sim.v[0], 'vy': sim.v[1], 'vz': sim.v[2], 's': sim.s, 'p': sim.p}
+        for k in names:
+            cur[k][0, H:H + nz].copy_(host[k].to(dev, non_blocking=True).permute(2, 1, 0))
+        sim.step()
+        cur = {'vx': sim.v[0], 'vy': sim.v[1], 'vz': sim.v[2], 's': sim.s, 'p': sim.p}
+        for k in names:
+            host[k].copy_(cur[k][0, H:H + nz].permute(2, 1, 0), non_blocking=True)
+    one()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        one()
+    t1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([t0.elapsed_time(t1) / steps], device=dev, dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return {"value": 1e3 / float(ms.item()), "unit": "steps/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": steps,
+            "note": "per rank: slab state (v, s, p) in pinned host arrays in reference (x,y,z) order; upload + transpose + step + transpose + download"}
+
+
 def run(args, metric):
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -71,6 +109,7 @@ def run(args, metric):
     vmax = torch.stack([c.abs().max() for c in sim.v]).max()
     dist.all_reduce(vmax, op=dist.ReduceOp.MAX)
     disp = float(vmax.item()) * DT / dx[0]
+    e2e = run_e2e(sim, slab, args, dev)
     if rank == 0:
         peak = 6572.9
         try:
@@ -91,7 +130,7 @@ def run(args, metric):
                 "roofline": {"bound": "hbm", "kernel": "k_cg_ring<3> (all ranks)", "achieved": cg_gbs, "peak": peak * world, "unit": "GB/s",
                              "frac": cg_gbs / (peak * world), "traffic": None,
                              "algorithmic_bytes": "cells*(32*iterations+32) per solve, aggregate over ranks"},
-                "e2e": None}
+                "e2e": e2e}
         assert disp < slab.halo - 1, f"advection halo too small: displacement {disp} cells, halo {slab.halo}"
         print(json.dumps(line))
     slab.close()
