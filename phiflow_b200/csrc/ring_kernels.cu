@@ -17,6 +17,7 @@
 // the common case runs a branch-free path: 5 LDS.128 + 2 SHFL + ~40 FP32 ops + 1 STG.128 per group.
 #include <cooperative_groups.h>
 #include "cg_common.cuh"
+#include <cstdlib>
 #include <cstring>
 #include "launch.cuh"
 
@@ -813,7 +814,10 @@ static bool ring_config(const DGrid& g, int lines_a, int lines_b, int reserve_by
     RingCfg c;
     c.pitch = g.cext[0]; c.nx4 = g.cext[0] / 4;
     const int row_bytes = c.pitch * 4;
-    int ty = g.dim == 3 ? 8 : 16;
+    // measured on B200 (512^3): TY=4 beats TY=8 for both laplace (6.12 vs 5.85 TB/s) and CG (5.18 vs 5.10 TB/s): smaller
+    // stages -> deeper ring; the extra y-halo lines are served by L2
+    int ty = g.dim == 3 ? 4 : 16;
+    if (const char* e = getenv("PHICUDA_RING_TY")) { const int v = atoi(e); if (v >= 1 && v <= ty) ty = v; }     // tuning knob
     for (;; ty /= 2) {
         if (ty < 1) return false;
         if (ty * c.nx4 > RING_G * RING_CONSUMERS) continue;                    // <= RING_G groups per thread
@@ -827,14 +831,24 @@ static bool ring_config(const DGrid& g, int lines_a, int lines_b, int reserve_by
     c.shfl_ok = (c.nx4 % 32 == 0) ? 1 : 0;
     if (g.dim == 3) {
         c.nyt = (g.n[1] + c.TY - 1) / c.TY;
-        int zc = g.n[2] < 64 ? g.n[2] : 64;
-        for (;;) {
-            c.ZC = zc; c.nzc = (g.n[2] + zc - 1) / zc;
-            c.units_per_batch = c.nyt * c.nzc;
-            c.total_units = c.units_per_batch * g.batch;
-            if (c.total_units >= target_units || zc <= 8) break;
-            zc /= 2;
+        // z chunking: every unit pays a pipeline refill + two halo planes (~ (ZC+2)/ZC), and the persistent grid of
+        // `ctas` CTAs is only fully busy when the unit count is close to a multiple of it -> maximise
+        //   utilisation(units, ctas) / (1 + 2/ZC)
+        const int ctas = target_units;
+        double best = -1.0; int best_nzc = 1;
+        const int max_nzc = g.n[2] >= 4 ? g.n[2] / 4 : 1;
+        for (int nzc = 1; nzc <= max_nzc; ++nzc) {
+            const int zc = (g.n[2] + nzc - 1) / nzc;
+            if ((g.n[2] + zc - 1) / zc != nzc) continue;
+            const long long units = (long long)c.nyt * nzc * g.batch;
+            const long long rounds = (units + ctas - 1) / ctas;
+            const double util = (double)units / (double)(rounds * ctas);
+            const double score = util / (1.0 + 2.0 / zc);
+            if (score > best + 1e-9) { best = score; best_nzc = nzc; }
         }
+        c.nzc = best_nzc; c.ZC = (g.n[2] + best_nzc - 1) / best_nzc;
+        c.units_per_batch = c.nyt * c.nzc;
+        c.total_units = c.units_per_batch * g.batch;
     } else {
         c.nyt = (g.n[1] + c.TY - 1) / c.TY; c.nzc = 1; c.ZC = 1;
         c.units_per_batch = c.nyt; c.total_units = c.nyt * g.batch;
@@ -865,7 +879,7 @@ int phi_launch_laplace_ring(const DGrid& g, const DField& f, const float* x, flo
     RingCfg cfg;
     const int sms = sm_count();
     // two CTAs per SM: each gets half of the shared memory
-    if (!ring_config(g, 1, 2, kSmemBudget / 2 + 1024, g.dim == 3 ? 4 : 2, 6, sms * 2 * 4, &cfg)) return -100;
+    if (!ring_config(g, 1, 2, kSmemBudget / 2 + 1024, g.dim == 3 ? 4 : 2, 6, sms * 2, &cfg)) return -100;
     const size_t smem = 128 + (size_t)cfg.R * cfg.stage_floats * 4;
     int grid = sms * 2;
     if (grid > cfg.total_units) grid = cfg.total_units;
@@ -890,7 +904,7 @@ int phi_launch_cg_ring(const CgLaunch& l, const CommDev* cm, cudaStream_t s)
     CgRingArgs A;
     const int cgs = (int)((cg_smem_bytes(g.batch) + 127) / 128 * 128);
     const int sms = sm_count();
-    if (!ring_config(g, 3, 4, cgs, g.dim == 3 ? 4 : 2, RING_MAX_STAGES, sms * 6, &A.cfg)) return -100;
+    if (!ring_config(g, 3, 4, cgs, g.dim == 3 ? 4 : 2, RING_MAX_STAGES, sms, &A.cfg)) return -100;
     A.ring_smem_offset = cgs;
     const size_t smem = (size_t)cgs + 128 + (size_t)A.cfg.R * A.cfg.stage_floats * 4;
     int per_sm = 0;

@@ -25,20 +25,23 @@ def timed(fn, reps):
 
 
 def main():
-    sizes = [int(a) for a in sys.argv[1:] if a.isdigit()] or [256, 512]
+    sizes = [a for a in sys.argv[1:] if a[0].isdigit()] or ['256', '512']
     dims2 = '--2d' in sys.argv
     for n in sizes:
-        for ring in (True, False):
+        for ring in ((True,) if '--ring-only' in sys.argv else (True, False)):
             os.environ['PHICUDA_NO_RING'] = '0' if ring else '1'
+            shape = tuple(int(v) for v in n.split('x'))
             if dims2:
                 vbc = (('periodic', 'periodic'),) * 2
                 batch = 64
-                dom = ops.Domain((n, n), (1.0, 1.0), batch, vbc=vbc)
-                cells = batch * n * n
+                shape = shape * 2 if len(shape) == 1 else shape
+                dom = ops.Domain(shape, (1.0, 1.0), batch, vbc=vbc)
+                cells = batch * shape[0] * shape[1]
             else:
                 vbc = (('periodic', 'periodic'),) * 3
-                dom = ops.Domain((n, n, n), (1.0, 1.0, 1.0), 1, vbc=vbc)
-                cells = n ** 3
+                shape = shape * 3 if len(shape) == 1 else shape
+                dom = ops.Domain(shape, (1.0, 1.0, 1.0), 1, vbc=vbc)
+                cells = shape[0] * shape[1] * shape[2]
             x = torch.randn(dom._shape(dom.cext), device='cuda')
             y = torch.empty_like(x)
             ms = timed(lambda: ops.laplace(dom, vbc, x, out=y), 20)
