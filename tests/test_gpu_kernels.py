@@ -352,3 +352,70 @@ def test_plume_step(vname, mac):
     div = dom.centered_to_numpy(ops.divergence(dom, vbc, dv))
     rhs_scale = vmax * sum(2.0 / h for h in dx)
     assert np.abs(div).max() < 1e-2 * rhs_scale
+
+
+def test_config_c1_smoke_plume_128_2d():
+    """BASELINE configs[0] (examples/grids/Smoke_Plume at 128x128, closed box, CG 1e-3 warm start): 8 steps vs the oracle."""
+    res = (128, 128)
+    lower, upper = (0.0, 0.0), (100.0, 100.0)
+    dx = (100.0 / 128, 100.0 / 128)
+    vbc, sbc = O.uniform_bc(2, 0.0), O.uniform_bc(2, 'zg')
+    inflow = O.sphere_soft_mask((50.0, 9.5), 5.0, lower, upper, res)
+    dom = ops.Domain(res, dx, 1, vbc=vbc)
+    v = [np.zeros(s, np.float32) for s in O.staggered_shapes(res, vbc)]
+    s = np.zeros(res, np.float32); p = np.zeros(res, np.float32)
+    dv, ds, dp = dom.faces_from_numpy(v, vbc), dom.centered_from_numpy(s), dom.centered_from_numpy(p)
+    dinflow = dom.centered_from_numpy(inflow)
+    prm = ops.cg_params(vbc, rtol=1e-3, atol=1e-5)
+    A = O.poisson_matrix(res, dx, O.pressure_bc(vbc))
+    for _ in range(8):
+        ops.plume_step(dom, vbc, sbc, dv, ds, dp, dinflow, 0.5, 0.2, (0.0, 0.1), prm, mac_cormack=True)
+        v, s, p, info = O.plume_step(v, s, p, 0.5, vbc, sbc, lower, upper, res, inflow, 0.2, (0.0, 0.1), rtol=1e-3, atol=1e-5,
+                                     smoke_advection='mac_cormack', use_matrix_offset=False, matrix=A)
+        assert ops.read_results(dom)['converged'][0] == 1 and info['converged']
+    got_s = dom.centered_to_numpy(ds)
+    np.testing.assert_allclose(got_s, s, rtol=0, atol=5e-4 * np.abs(s).max())
+    got = dom.faces_to_numpy(dv, vbc)
+    vmax = max(np.abs(c).max() for c in v)
+    for c in range(2):
+        np.testing.assert_allclose(got[c], v[c], rtol=0, atol=2e-2 * vmax)
+    assert np.abs(s).max() > 0.5 and vmax > 1e-2
+
+
+def test_config_c3_taylor_green_3d():
+    """BASELINE configs[2] at 32^3: Taylor-Green vortex on [0, 2pi]^3, periodic, steps of semi_lagrangian -> make_incompressible;
+    gates: divergence after projection, agreement with the oracle, kinetic energy does not grow."""
+    n = 32
+    res = (n, n, n)
+    L = 2 * np.pi
+    dx = (L / n,) * 3
+    lower, upper = (0.0,) * 3, (L,) * 3
+    vbc = O.uniform_bc(3, 'periodic')
+    ax = np.arange(n, dtype=np.float64) * dx[0]
+    cc = ax + 0.5 * dx[0]
+    X, Y, Z = np.meshgrid(ax, cc, cc, indexing='ij')
+    u = (np.sin(X) * np.cos(Y) * np.cos(Z)).astype(np.float32)              # x-faces: (face x, centre y, centre z)
+    X, Y, Z = np.meshgrid(cc, ax, cc, indexing='ij')
+    w = (-np.cos(X) * np.sin(Y) * np.cos(Z)).astype(np.float32)
+    v = [u, w, np.zeros(res, np.float32)]
+    dom = ops.Domain(res, dx, 1, vbc=vbc)
+    dv = dom.faces_from_numpy(v, vbc)
+    dp = dom.alloc_centered()
+    prm = ops.cg_params(vbc, rtol=1e-5, atol=1e-6)
+    A = O.poisson_matrix(res, dx, O.pressure_bc(vbc))
+    dt = 0.5 * dx[0]
+    energy = [sum(float(np.sum(c.astype(np.float64) ** 2)) for c in v)]
+    p = np.zeros(res, np.float32)
+    for _ in range(3):
+        dv2 = ops.advect_staggered(dom, vbc, dv, vbc, dv, dt)
+        dv, dp = ops.make_incompressible(dom, vbc, dv2, dp, prm)
+        v = O.semi_lagrangian_staggered(v, vbc, v, vbc, res, lower, upper, dt)
+        v, p, info = O.make_incompressible(v, vbc, res, dx, rtol=1e-5, atol=1e-6, x0=p, use_matrix_offset=False, matrix=A)
+        got = dom.faces_to_numpy(dv, vbc)
+        energy.append(sum(float(np.sum(c.astype(np.float64) ** 2)) for c in got))
+    div = dom.centered_to_numpy(ops.divergence(dom, vbc, dv))
+    assert np.abs(div).max() <= 5e-5 * 1.0 / dx[0]
+    for c in range(3):
+        np.testing.assert_allclose(got[c], v[c], rtol=0, atol=2e-4)
+    assert all(b <= a * (1 + 1e-6) for a, b in zip(energy, energy[1:]))
+    assert abs(energy[-1] / energy[0] - 1) < 0.05

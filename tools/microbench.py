@@ -58,8 +58,17 @@ def main():
             info = ops.read_results(dom)
             it = float(np.mean(info['iterations']))
             cg = cells * (32.0 * it + 32.0) / ms_cg / 1e6
+            adv = ''
+            if ring:
+                v = [0.3 * torch.randn(dom._shape(dom.fext), device='cuda') for _ in range(dom.dim)]
+                v2 = dom.alloc_faces()
+                sbc = (('zg', 'zg'),) * dom.dim
+                ms_a = timed(lambda: ops.advect_staggered(dom, vbc, v, vbc, v, 0.5, out=v2), 5)
+                ms_c = timed(lambda: ops.advect_centered(dom, vbc, v, sbc, rhs, 0.5, out=y), 5)
+                adv = f" | advect staggered {ms_a:.3f} ms = {20.0 * dom.dim * cells / ms_a / 1e6:.0f} GB/s, centred {ms_c:.3f} ms = {20.0 * cells / ms_c / 1e6:.0f} GB/s"
+                del v, v2
             print(f"n={n} {'2d x64' if dims2 else '3d'} ring={int(ring)}: laplace {ms:.4f} ms = {lap:.0f} GB/s | "
-                  f"CG {it:.0f} it in {ms_cg:.2f} ms = {ms_cg / max(it, 1) * 1e3:.1f} us/it = {cg:.0f} GB/s (32 B/cell/it)", flush=True)
+                  f"CG {it:.0f} it in {ms_cg:.2f} ms = {ms_cg / max(it, 1) * 1e3:.1f} us/it = {cg:.0f} GB/s (32 B/cell/it){adv}", flush=True)
             del x, y, rhs, p, dom
             torch.cuda.empty_cache()
 
