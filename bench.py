@@ -36,33 +36,7 @@ def load_peaks():
     return 6650.0, 'fallback'
 
 
-class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    QUERY = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
-            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
-
-    def __init__(self, index=0):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
-
-    def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.check_output(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits',
-                                               '-i', str(self.index)], timeout=5).decode().strip()
-                self.samples.append([v.strip() for v in out.split(',')])
-            except Exception:
-                pass
-            time.sleep(0.2)
-
-    def summary(self):
-        self.stop_flag = True
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i] == 'Active' for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(sm)}
+from phiflow_b200._clocks import ClockSampler  # noqa: E402
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -846,6 +846,10 @@ static bool ring_config(const DGrid& g, int lines_a, int lines_b, int reserve_by
             const double score = util / (1.0 + 2.0 / zc);
             if (score > best + 1e-9) { best = score; best_nzc = nzc; }
         }
+        if (const char* e = getenv("PHICUDA_RING_NZC")) {                     // tuning knob
+            const int v = atoi(e);
+            if (v >= 1 && v <= g.n[2]) { const int zc = (g.n[2] + v - 1) / v; best_nzc = (g.n[2] + zc - 1) / zc; }
+        }
         c.nzc = best_nzc; c.ZC = (g.n[2] + best_nzc - 1) / best_nzc;
         c.units_per_batch = c.nyt * c.nzc;
         c.total_units = c.units_per_batch * g.batch;

@@ -8,6 +8,7 @@ import torch.distributed as dist
 
 from . import _ops as ops
 from .dist import Slab, SlabPlume
+from ._clocks import ClockSampler
 
 DT, INFLOW_RATE, BUOYANCY = 0.5, 0.2, (0.0, 0.0, 0.1)
 RTOL, ATOL, MAX_ITER = 1e-3, 1e-5, 1000
@@ -90,6 +91,9 @@ def run(args, metric):
     dist.barrier()
     torch.cuda.synchronize()
     cg_events = []
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     for i in range(args.steps):
@@ -97,6 +101,7 @@ def run(args, metric):
         iters_host[args.warmup + i].copy_(slab.result_tensor()[:6], non_blocking=True)
     end.record()
     torch.cuda.synchronize()
+    clocks = sampler.summary() if sampler else None
     dist.barrier()
     torch.cuda.synchronize()
     ms_local = torch.tensor([start.elapsed_time(end)], device=dev, dtype=torch.float64)
@@ -126,7 +131,7 @@ def run(args, metric):
                            "halo_planes": slab.halo, "max_displacement_cells": disp,
                            "comm": "CG: in-kernel NVLink peer stores (halo planes + mailbox all-reduce); other halos: NCCL send/recv",
                            "l2": "arrays exceed L2, no flush"},
-                "gpu_launches": sim.launches_per_step * args.steps,
+                "clocks": clocks, "gpu_launches": sim.launches_per_step * args.steps * world,
                 "roofline": {"bound": "hbm", "kernel": "k_cg_ring<3> (all ranks)", "achieved": cg_gbs, "peak": peak * world, "unit": "GB/s",
                              "frac": cg_gbs / (peak * world), "traffic": None,
                              "algorithmic_bytes": "cells*(32*iterations+32) per solve, aggregate over ranks"},
