@@ -592,3 +592,79 @@ def plume_step(v, s, p, dt, vbc, sbc, lower, upper, res, inflow_mask, inflow_rat
     v_new, p_new, info = make_incompressible(v_b, vbc, res, dx, rtol, atol, max_iter, x0=p,
                                              use_matrix_offset=use_matrix_offset, rng=rng, matrix=matrix)
     return v_new, s_new, p_new, info
+
+
+# --------------------------------------------------------------------------------------------------
+# N4  static obstacles: accessible / hard_bcs masks (phi/physics/fluid.py:130-137, 165-202, 212-240)
+# --------------------------------------------------------------------------------------------------
+
+def accessible_bc(vbc) -> tuple:
+    """fluid._accessible_extrapolation (phi/physics/fluid.py:277-288): PERIODIC -> PERIODIC, BOUNDARY -> ONE, constant -> ZERO."""
+    def conv(side):
+        if side == PERIODIC:
+            return PERIODIC
+        return 1.0 if side == ZG else 0.0
+    return tuple((conv(lo), conv(hi)) for lo, hi in vbc)
+
+
+def hard_bcs_faces(accessible: np.ndarray, vbc) -> List[np.ndarray]:
+    """field.stagger(accessible, math.minimum, velocity.boundary, at='face') (fluid.py:134, _field_math.py:535-581):
+    1 on faces between two accessible cells, 0 on faces touching an obstacle; ghost cells from accessible_bc."""
+    abc = accessible_bc(vbc)
+    out = []
+    for c in range(accessible.ndim):
+        lo, hi = valid_outer_faces(vbc, c)
+        if lo and hi:
+            wl, wu = (1, 0), (0, 1)
+        elif lo and not hi:
+            wl, wu = (1, -1), (0, 0)
+        elif (not lo) and hi:
+            wl, wu = (0, 0), (-1, 1)
+        else:
+            wl, wu = (0, -1), (-1, 0)
+        lower = pad_axis(accessible.astype(F32), c, wl[0], wl[1], abc[c])
+        upper = pad_axis(accessible.astype(F32), c, wu[0], wu[1], abc[c])
+        out.append(np.minimum(lower, upper))
+    return out
+
+
+def masked_poisson_matrix(res, dx, vbc, accessible: np.ndarray) -> sp.csr_matrix:
+    """Matrix of fluid.masked_laplace with obstacles (fluid.py:197-202): div(hard_bcs * grad p) on active cells,
+    identity on inactive ones (`where(active, div, pressure)`).  Built column-block-wise from the oracle's own
+    gradient / divergence so that it follows the same restated glue (validated against a phiml-traced matrix)."""
+    d = len(res)
+    pbc = pressure_bc(vbc)
+    vbc0 = tuple(tuple(0.0 if is_const(s) else s for s in ax) for ax in vbc)      # remove_constant_offset
+    hard = hard_bcs_faces(accessible, vbc)
+    n = int(np.prod(res))
+    cols = []
+    eye = np.eye(n, dtype=F32)
+    for j in range(n):
+        pj = eye[j].reshape(res)
+        grad = gradient_faces(pj, dx, pbc, vbc0)
+        grad = [g * h for g, h in zip(grad, hard)]
+        div = divergence_staggered(grad, dx, component_bcs(vbc0, d))
+        cols.append(np.where(accessible > 0, div, pj).ravel())
+    return sp.csr_matrix(np.stack(cols, 1).astype(F32))
+
+
+def make_incompressible_obstacles(v: List[np.ndarray], vbc, res, dx, accessible: np.ndarray, vmask: List[np.ndarray] = None,
+                                  rtol=1e-5, atol=1e-5, max_iter=1000, x0=None, matrix=None):
+    """fluid.make_incompressible with stationary obstacles (phi/physics/fluid.py:121-162):
+    v <- v * (1 - obstacle mask at faces) [apply_boundary_conditions, :212-240], div *= active, balanced with
+    div - active*mean(div)/mean(active) [:205-209], masked CG, v -= hard_bcs * grad p."""
+    d = len(res)
+    accessible = accessible.astype(F32)
+    if vmask is not None:
+        v = [a * m for a, m in zip(v, vmask)]
+    div = divergence_staggered(v, dx, component_bcs(vbc, d)) * accessible
+    if not is_flexible(vbc):
+        div = div - accessible * (np.mean(div, dtype=F32) / np.mean(accessible, dtype=F32))
+    A = matrix if matrix is not None else masked_poisson_matrix(res, dx, vbc, accessible)
+    x0 = np.zeros(res, F32) if x0 is None else x0
+    info = cg(A, div, x0, rtol, atol, max_iter, None)
+    p = info['x'].reshape(res)
+    grad = gradient_faces(p, dx, pressure_bc(vbc), vbc)
+    hard = hard_bcs_faces(accessible, vbc)
+    v_new = [a - g * h for a, g, h in zip(v, grad, hard)]
+    return v_new, p, info

@@ -237,6 +237,63 @@ def main():
         out[f'cg/{name}/dx'] = np.array(dx)
         out[f'cg/{name}/rhs'] = rhs
 
+    # 6. static obstacles: hard_bcs = stagger(accessible, minimum), masked_laplace with where(active, div, p)
+    def accessible_ext(spec):
+        conv = lambda s_: 'periodic' if s_ == 'periodic' else (1.0 if s_ == 'zg' else 0.0)
+        return tuple((conv(lo), conv(hi)) for lo, hi in spec)
+
+    def hard_bcs(acc, aext, vext):
+        comps = []
+        for dim in acc.shape.spatial.names:
+            lo, up = vext.valid_outer_faces(dim)
+            if lo and up:
+                wl, wu = {dim: (1, 0)}, {dim: (0, 1)}
+            elif lo and not up:
+                wl, wu = {dim: (1, -1)}, {dim: (0, 0)}
+            elif not lo and up:
+                wl, wu = {dim: (0, 0)}, {dim: (-1, 1)}
+            else:
+                wl, wu = {dim: (0, -1)}, {dim: (-1, 0)}
+            comps.append(math.minimum(math.pad(acc, wl, aext), math.pad(acc, wu, aext)))
+        return comps
+
+    def masked_laplace_obs(p, dx, pext, vext0, hard, active):
+        grad = [g_ * h_ for g_, h_ in zip(stagger_grad(p, dx, pext, vext0), hard)]
+        return math.where(active, staggered_divergence(grad, dx, vext0), p)
+
+    for name, spec in [('zero', BC_SETS_2D['zero']), ('open', BC_SETS_2D['open']), ('periodic', BC_SETS_2D['periodic']),
+                       ('mixed', BC_SETS_2D['mixed']), ('zero3', BC_SETS_3D['zero']), ('periodic3', BC_SETS_3D['periodic'])]:
+        d = len(spec)
+        res = (7, 6) if d == 2 else (5, 4, 4)
+        dx = (0.5, 0.25) if d == 2 else (0.5, 0.25, 2.0)
+        acc = np.ones(res, np.float32)
+        if d == 2:
+            acc[2:4, 1:4] = 0
+        else:
+            acc[1:3, 1:3, 1:3] = 0
+        vext = ext_from_spec(spec)
+        vext0 = ext_from_spec(remove_const(spec))
+        pext = ext_from_spec(pressure_ext(spec))
+        aext = ext_from_spec(accessible_ext(spec))
+        hard = hard_bcs(to_tensor(acc), aext, vext)
+        pr = rng.standard_normal(res).astype(np.float32)
+        out[f'obst/{name}/bc'] = spec_to_arr(spec)
+        out[f'obst/{name}/dx'] = np.array(dx)
+        out[f'obst/{name}/accessible'] = acc
+        for c in range(d):
+            out[f'obst/{name}/hard{c}'] = npy(hard[c], d)
+        out[f'obst/{name}/p'] = pr
+        active = to_tensor(acc)
+        out[f'obst/{name}/lap_p'] = npy(masked_laplace_obs(to_tensor(pr), dx, pext, vext0, hard, active), d)
+        try:
+            lin = math.jit_compile_linear(masked_laplace_obs, auxiliary_args='dx,pext,vext0,hard,active')
+            mat = lin.sparse_matrix(to_tensor(pr), dx=dx, pext=pext, vext0=vext0, hard=hard, active=active)
+            n_tot = int(np.prod(res))
+            order_ = ','.join(NAMES[:d]) + ',' + ','.join('~' + n_ for n_ in NAMES[:d])
+            out[f'obst/{name}/matrix'] = math.dense(mat).numpy(order_).reshape(n_tot, n_tot)
+        except Exception as err:
+            print(f"masked matrix tracing failed for '{name}': {type(err).__name__}: {err}")
+
     np.savez_compressed(os.path.join(OUT, 'phiml_golden.npz'), **out)
     print(f"wrote {len(out)} arrays to {os.path.join(OUT, 'phiml_golden.npz')}")
 

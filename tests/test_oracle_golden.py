@@ -210,3 +210,22 @@ def test_make_incompressible_removes_divergence(vbc):
         assert info['converged']
     div = O.divergence_staggered(v, dx, O.component_bcs(vbc, 2))
     assert np.abs(div).max() < 5e-5
+
+
+@pytest.mark.parametrize('name', names('obst'))
+def test_obstacle_masks_and_masked_laplace_match_phiml(name):
+    """hard_bcs = stagger(accessible, minimum) and masked_laplace with where(active, div, p)
+    (phi/physics/fluid.py:130-137, 197-202), traced to a matrix by the reference's own jit_compile_linear."""
+    vbc = spec_from_arr(GOLD[f'obst/{name}/bc'])
+    dx = GOLD[f'obst/{name}/dx']
+    acc = GOLD[f'obst/{name}/accessible']
+    d = acc.ndim
+    hard = O.hard_bcs_faces(acc, vbc)
+    for c in range(d):
+        np.testing.assert_array_equal(hard[c], GOLD[f'obst/{name}/hard{c}'])
+    A = O.masked_poisson_matrix(acc.shape, dx, vbc, acc)
+    p = GOLD[f'obst/{name}/p']
+    ref = GOLD[f'obst/{name}/lap_p']
+    np.testing.assert_allclose(A.dot(p.ravel()).reshape(acc.shape), ref, rtol=0, atol=4e-6 * np.abs(ref).max())
+    if f'obst/{name}/matrix' in GOLD.files:
+        np.testing.assert_allclose(A.toarray(), GOLD[f'obst/{name}/matrix'], rtol=1e-6, atol=1e-6)
