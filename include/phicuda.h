@@ -163,6 +163,19 @@ int phicuda_make_incompressible_f32(const PhiGrid* g, const PhiVBC* vbc, float* 
                                     const PhiCgParams* prm, PhiCgResult* result, void* workspace,
                                     size_t workspace_bytes, void* stream);
 
+/* ---- N4  static obstacles (phi/physics/fluid.py:121-137, 165-202, 212-240) ---------------------------------------------
+ * accessible: centred mask, 1 in fluid cells, 0 inside obstacles (`~union(obstacle geometries)` sampled at cell centres).
+ * make_incompressible_masked = divergence * active, CG on masked_laplace (faces touching an obstacle carry no flux,
+ * obstacle cells are identity rows), v -= hard_bcs * grad p.  The caller applies apply_boundary_conditions first
+ * (v *= 1 - obstacle mask at faces: phicuda_mul_faces_f32).  Runs on the register-marching CG kernel. */
+int phicuda_mul_faces_f32(const PhiGrid* g, const PhiVBC* vbc, float* const v[3], const float* const mask[3], void* stream);
+int phicuda_cg_poisson_masked_f32(const PhiGrid* g, const PhiVBC* vbc, const float* rhs, float* x, const float* accessible,
+                                  const PhiCgParams* prm, PhiCgResult* result, void* workspace, size_t workspace_bytes,
+                                  void* stream);
+int phicuda_make_incompressible_masked_f32(const PhiGrid* g, const PhiVBC* vbc, float* const v[3], float* p, float* div,
+                                           const float* accessible, const PhiCgParams* prm, PhiCgResult* result,
+                                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- incompressible_step: the fused notebook step -----------------------------------------------
  * s' = advect(s, v, dt) + inflow_rate * inflow ; v* = semi_lagrangian(v, v, dt) + dt * buoyancy(s') ;
  * v', p' = make_incompressible(v*, Solve('CG', x0 = p)).   mac_cormack != 0 selects advect.mac_cormack for s.

@@ -65,6 +65,11 @@ PROTOTYPES = {
                                          C.c_void_p, C.c_size_t, C.c_void_p]),
     'phicuda_make_incompressible_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), F3, C.c_void_p, C.c_void_p, _P(PhiCgParams),
                                                   C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'phicuda_mul_faces_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), F3, F3, C.c_void_p]),
+    'phicuda_cg_poisson_masked_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), C.c_void_p, C.c_void_p, C.c_void_p, _P(PhiCgParams),
+                                                C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'phicuda_make_incompressible_masked_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), F3, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                         _P(PhiCgParams), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'phicuda_comm_create': (C.c_int, [C.c_int, C.c_int, _P(PhiGrid), _P(C.c_void_p), C.c_void_p]),
     'phicuda_comm_connect': (C.c_int, [C.c_void_p, C.c_void_p]),
     'phicuda_comm_destroy': (C.c_int, [C.c_void_p]),

@@ -299,13 +299,25 @@ def cg_poisson(dom: Domain, vbc, rhs, x0=None, prm: PhiCgParams = None):
     return x
 
 
-def make_incompressible(dom: Domain, vbc, v, p=None, prm: PhiCgParams = None):
-    """fluid.make_incompressible on raw arrays: v and p are updated in place."""
+def mul_faces(dom: Domain, vbc, v, mask):
+    """v_c *= mask_c on the stored faces (apply_boundary_conditions for stationary obstacles, fluid.py:212-240)."""
+    require_cuda()
+    _lib.check(_lib.load().phicuda_mul_faces_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(v, dom.foff), _f3(mask, dom.foff), _stream()))
+    return v
+
+
+def make_incompressible(dom: Domain, vbc, v, p=None, prm: PhiCgParams = None, accessible=None):
+    """fluid.make_incompressible on raw arrays: v and p are updated in place.  accessible: centred obstacle mask (N4)."""
     require_cuda()
     ws, res = dom.workspace()
     p = dom.alloc_centered() if p is None else p
     div = dom.alloc_centered()
     prm = prm or cg_params(vbc)
+    if accessible is not None:
+        _lib.check(_lib.load().phicuda_make_incompressible_masked_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(v, dom.foff),
+                                                                      _ptr(p, dom.coff), _ptr(div, dom.coff), _ptr(accessible, dom.coff),
+                                                                      C.byref(prm), _ptr(res), _ptr(ws), C.c_size_t(ws.numel()), _stream()))
+        return v, p
     _lib.check(_lib.load().phicuda_make_incompressible_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(v, dom.foff), _ptr(p, dom.coff), _ptr(div, dom.coff),
                                                            C.byref(prm), _ptr(res), _ptr(ws), C.c_size_t(ws.numel()), _stream()))
     return v, p

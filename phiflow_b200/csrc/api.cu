@@ -208,7 +208,7 @@ int phicuda_divergence_f32(const PhiGrid* g, const PhiVBC* vbc, const float* con
     DGrid dg; DVec dv; DField cf; PhiBC none; memset(&none, 0, sizeof(none));
     CHECK(phi_make_dgrid(g, &dg)); CHECK(make_vec(g, vbc, v, &dv)); CHECK(phi_make_centered(g, &none, &cf));
     if (!div) { phi_set_error("divergence: div is NULL"); return PHI_ERR_INVALID; }
-    return cuda_fail(phi_launch_divergence(dg, dv, cf, div, (cudaStream_t)stream), "divergence");
+    return cuda_fail(phi_launch_divergence(dg, dv, cf, div, nullptr, (cudaStream_t)stream), "divergence");
 }
 
 int phicuda_grad_sub_f32(const PhiGrid* g, const PhiVBC* vbc, float* const v[3], const float* p, void* stream)
@@ -218,7 +218,7 @@ int phicuda_grad_sub_f32(const PhiGrid* g, const PhiVBC* vbc, float* const v[3],
     CHECK(phi_pressure_bc(vbc, g->dim, &pbc)); CHECK(phi_make_centered(g, &pbc, &pf));
     if (!p) { phi_set_error("grad_sub: p is NULL"); return PHI_ERR_INVALID; }
     for (int c = 0; c < 3; ++c) out.p[c] = c < g->dim ? v[c] : nullptr;
-    return cuda_fail(phi_launch_grad_sub(dg, dv, out, pf, p, (cudaStream_t)stream), "grad_sub");
+    return cuda_fail(phi_launch_grad_sub(dg, dv, out, pf, p, nullptr, nullptr, (cudaStream_t)stream), "grad_sub");
 }
 
 int phicuda_advect_centered_f32(const PhiGrid* g, const PhiVBC* vbc, const float* const vel[3],
@@ -270,6 +270,56 @@ int phicuda_add_buoyancy_f32(const PhiGrid* g, const PhiVBC* vbc, const PhiBC* s
     if (!s || !b) { phi_set_error("add_buoyancy: NULL argument"); return PHI_ERR_INVALID; }
     for (int c = 0; c < 3; ++c) out.p[c] = c < g->dim ? v[c] : nullptr;
     return cuda_fail(phi_launch_buoyancy(dg, dv, out, sf, s, b, dt, (cudaStream_t)stream), "add_buoyancy");
+}
+
+// ---- N4: static obstacles ------------------------------------------------------------------------------------------------
+static int accessible_field(const PhiGrid* g, const PhiVBC* vbc, DField* af)
+{
+    // fluid._accessible_extrapolation (phi/physics/fluid.py:277-288): PERIODIC -> PERIODIC, BOUNDARY -> ONE, constant -> ZERO
+    PhiBC abc; memset(&abc, 0, sizeof(abc));
+    for (int a = 0; a < g->dim; ++a) {
+        const uint8_t kl = vbc->comp[a].lo[a], kh = vbc->comp[a].hi[a];
+        abc.lo[a] = kl == PHI_BC_PERIODIC ? PHI_BC_PERIODIC : PHI_BC_CONST; abc.clo[a] = kl == PHI_BC_ZERO_GRADIENT ? 1.f : 0.f;
+        abc.hi[a] = kh == PHI_BC_PERIODIC ? PHI_BC_PERIODIC : PHI_BC_CONST; abc.chi[a] = kh == PHI_BC_ZERO_GRADIENT ? 1.f : 0.f;
+        if (kl == PHI_BC_HALO || kh == PHI_BC_HALO) { phi_set_error("obstacles are not supported on z-slabs yet"); return PHI_ERR_UNSUPPORTED; }
+    }
+    return phi_make_centered(g, &abc, af);
+}
+
+int phicuda_mul_faces_f32(const PhiGrid* g, const PhiVBC* vbc, float* const v[3], const float* const mask[3], void* stream)
+{
+    DGrid dg; DVec dv; DVecOut out;
+    CHECK(phi_make_dgrid(g, &dg)); CHECK(make_vec(g, vbc, v, &dv));
+    for (int c = 0; c < 3; ++c) { out.p[c] = c < g->dim ? v[c] : nullptr; if (c < g->dim && !mask[c]) { phi_set_error("mul_faces: mask[%d] is NULL", c); return PHI_ERR_INVALID; } }
+    return cuda_fail(phi_launch_mul_faces(dg, dv, out, mask, (cudaStream_t)stream), "mul_faces");
+}
+
+int phicuda_cg_poisson_masked_f32(const PhiGrid* g, const PhiVBC* vbc, const float* rhs, float* x, const float* accessible,
+                                  const PhiCgParams* prm, PhiCgResult* result, void* workspace, size_t workspace_bytes, void* stream)
+{
+    CgLaunch l; PhiBC pbc; DField af;
+    CHECK(phi_make_dgrid(g, &l.g));
+    if (!vbc || !rhs || !x || !prm || !result || !workspace || !accessible) { phi_set_error("cg_masked: NULL argument"); return PHI_ERR_INVALID; }
+    CHECK(accessible_field(g, vbc, &af));
+    CHECK(phi_pressure_bc(vbc, g->dim, &pbc)); CHECK(phi_make_centered(g, &pbc, &l.pf));
+    l.rhs = rhs; l.x = x; l.prm = *prm; l.result = result; l.workspace = workspace; l.workspace_bytes = workspace_bytes;
+    l.acc = accessible;
+    return phi_launch_cg(l, (cudaStream_t)stream);
+}
+
+int phicuda_make_incompressible_masked_f32(const PhiGrid* g, const PhiVBC* vbc, float* const v[3], float* p, float* div,
+                                           const float* accessible, const PhiCgParams* prm, PhiCgResult* result,
+                                           void* workspace, size_t workspace_bytes, void* stream)
+{
+    DGrid dg; DVec dv; DVecOut out; DField cf, af, pf; PhiBC none, pbc; memset(&none, 0, sizeof(none));
+    CHECK(phi_make_dgrid(g, &dg)); CHECK(make_vec(g, vbc, v, &dv)); CHECK(phi_make_centered(g, &none, &cf));
+    if (!accessible || !p || !div) { phi_set_error("make_incompressible_masked: NULL argument"); return PHI_ERR_INVALID; }
+    CHECK(accessible_field(g, vbc, &af));
+    CHECK(phi_pressure_bc(vbc, g->dim, &pbc)); CHECK(phi_make_centered(g, &pbc, &pf));
+    for (int c = 0; c < 3; ++c) out.p[c] = c < g->dim ? v[c] : nullptr;
+    CHECK(cuda_fail(phi_launch_divergence(dg, dv, cf, div, accessible, (cudaStream_t)stream), "divergence"));       // div *= active
+    CHECK(phicuda_cg_poisson_masked_f32(g, vbc, div, p, accessible, prm, result, workspace, workspace_bytes, stream));
+    return cuda_fail(phi_launch_grad_sub(dg, dv, out, pf, p, &af, accessible, (cudaStream_t)stream), "grad_sub");   // grad *= hard_bcs
 }
 
 size_t phicuda_cg_workspace_bytes(const PhiGrid* g)

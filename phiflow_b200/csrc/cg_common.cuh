@@ -8,6 +8,7 @@
 struct CgArgs {
     DGrid g; DField pf; UnitMap um;
     const float* rhs; float* x; float* r; float* d0; float* d1;
+    const float* acc;              // N4: accessible mask (1 = fluid, 0 = obstacle) or nullptr
     double* partials;              // [2 regions][2 accumulators][batch][grid]
     PhiCgResult* result;
     PhiCgParams prm;

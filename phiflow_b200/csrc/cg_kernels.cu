@@ -48,11 +48,14 @@ struct SrcDirection {          // d' = r + beta*d
 struct EpiResidual0 {          // r = (rhs - mean) - A x0 [- c*sum(x0)];  acc0 = |r|^2, acc1 = |r without offset|^2
     const float* rhs; float* r; float mean; float offs;
     float acc0, acc1;
+    const float* accm;             // N4: balanced rhs is  div - accessible * mean(div)/mean(accessible)  (fluid.py:205-209)
     __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid)
     {
         const float4 y = *reinterpret_cast<const float4*>(rhs + off);
+        float4 mm = f4_splat(mean);
+        if (accm) { const float4 a4 = *reinterpret_cast<const float4*>(accm + off); mm = make_float4(mean * a4.x, mean * a4.y, mean * a4.z, mean * a4.w); }
         float4 rt;                                    // residual without offset (tolerance reference, _linalg.py:61-67)
-        rt.x = (y.x - mean) - q.x; rt.y = (y.y - mean) - q.y; rt.z = (y.z - mean) - q.z; rt.w = (y.w - mean) - q.w;
+        rt.x = (y.x - mm.x) - q.x; rt.y = (y.y - mm.y) - q.y; rt.z = (y.z - mm.z) - q.z; rt.w = (y.w - mm.w) - q.w;
         float4 rr = make_float4(rt.x - offs, rt.y - offs, rt.z - offs, rt.w - offs);
         if (nvalid == 4) {
             *reinterpret_cast<float4*>(r + off) = rr;
@@ -121,7 +124,7 @@ __device__ __forceinline__ void for_unit_cells(const DGrid& g, const DField& pf,
 
 // ---- the solver ---------------------------------------------------------------------------------------------
 
-template <int DIM>
+template <int DIM, bool MASK>
 __global__ void __launch_bounds__(PHI_WARPS_PER_CTA * 32, 2)
 k_cg_poisson(CgArgs a)
 {
@@ -164,13 +167,13 @@ k_cg_poisson(CgArgs a)
     if (a.prm.balance_rhs || coffs != 0.f) {
         sweep(nullptr, [&](const WarpUnit& w, float& acc0, float& acc1) {
             for_unit_cells<DIM>(g, a.pf, w, [&](long long off, int nvalid) {
-                for (int j = 0; j < nvalid; ++j) { acc0 += a.rhs[off + j]; acc1 += a.x[off + j]; }
+                for (int j = 0; j < nvalid; ++j) { acc0 += a.rhs[off + j]; acc1 += MASK ? a.acc[off + j] : a.x[off + j]; }
             });
         });
         barrier_and_reduce(nullptr);
         for (int b = threadIdx.x; b < batch; b += blockDim.x) {
-            sh.mean[b] = a.prm.balance_rhs ? (float)(sh.sum0[b] / cells) : 0.f;
-            sh.offs[b] = coffs * (float)sh.sum1[b];
+            if (MASK) { sh.mean[b] = (a.prm.balance_rhs && sh.sum1[b] > 0.0) ? (float)(sh.sum0[b] / sh.sum1[b]) : 0.f; sh.offs[b] = 0.f; }
+            else { sh.mean[b] = a.prm.balance_rhs ? (float)(sh.sum0[b] / cells) : 0.f; sh.offs[b] = coffs * (float)sh.sum1[b]; }
         }
         __syncthreads();
     }
@@ -178,8 +181,9 @@ k_cg_poisson(CgArgs a)
     // ---- r0 = y - (A + c 11^T) x0,  delta0 -----------------------------------------------------------------------
     sweep(nullptr, [&](const WarpUnit& w, float& acc0, float& acc1) {
         SrcArray src{a.x};
-        EpiResidual0 epi{a.rhs, a.r, sh.mean[w.b], sh.offs[w.b], 0.f, 0.f};
-        phi_march<DIM>(g, a.pf, src, epi, w.b, w.xt0, w.t, w.m0, w.m1);
+        EpiResidual0 epi{a.rhs, a.r, sh.mean[w.b], sh.offs[w.b], 0.f, 0.f, MASK ? a.acc : nullptr};
+        if (MASK) phi_march_masked<DIM>(g, a.pf, src, a.acc, epi, w.b, w.xt0, w.t, w.m0, w.m1);
+        else      phi_march<DIM>(g, a.pf, src, epi, w.b, w.xt0, w.t, w.m0, w.m1);
         acc0 += epi.acc0; acc1 += epi.acc1;
     });
     barrier_and_reduce(nullptr);
@@ -204,7 +208,8 @@ k_cg_poisson(CgArgs a)
         sweep(sh.cont, [&](const WarpUnit& w, float& acc0, float& acc1) {
             SrcDirection src{a.r, dold, sh.beta[w.b]};
             EpiPassA epi{dnew, 0.f, 0.f};
-            phi_march<DIM>(g, a.pf, src, epi, w.b, w.xt0, w.t, w.m0, w.m1);
+            if (MASK) phi_march_masked<DIM>(g, a.pf, src, a.acc, epi, w.b, w.xt0, w.t, w.m0, w.m1);
+            else      phi_march<DIM>(g, a.pf, src, epi, w.b, w.xt0, w.t, w.m0, w.m1);
             acc0 += epi.acc0; acc1 += epi.acc1;
         });
         barrier_and_reduce(sh.cont);
@@ -220,7 +225,8 @@ k_cg_poisson(CgArgs a)
         sweep(sh.cont, [&](const WarpUnit& w, float& acc0, float& acc1) {
             SrcArray src{dnew};
             EpiPassB epi{a.x, a.r, sh.alpha[w.b], sh.offs[w.b], 0.f, 0.f};
-            phi_march<DIM>(g, a.pf, src, epi, w.b, w.xt0, w.t, w.m0, w.m1);
+            if (MASK) phi_march_masked<DIM>(g, a.pf, src, a.acc, epi, w.b, w.xt0, w.t, w.m0, w.m1);
+            else      phi_march<DIM>(g, a.pf, src, epi, w.b, w.xt0, w.t, w.m0, w.m1);
             acc0 += epi.acc0;
         });
         barrier_and_reduce(sh.cont);
@@ -247,16 +253,16 @@ k_cg_poisson(CgArgs a)
     if (a.prm.project_mean) {
         sweep(nullptr, [&](const WarpUnit& w, float& acc0, float& acc1) {
             for_unit_cells<DIM>(g, a.pf, w, [&](long long off, int nvalid) {
-                for (int j = 0; j < nvalid; ++j) acc0 += a.x[off + j];
+                for (int j = 0; j < nvalid; ++j) { if (MASK) { acc0 += a.x[off + j] * a.acc[off + j]; acc1 += a.acc[off + j]; } else acc0 += a.x[off + j]; }
             });
         });
         barrier_and_reduce(nullptr);
         for (int unit = blockIdx.x; unit < um.total_units; unit += gridDim.x) {
             const WarpUnit w = phi_warp_unit<DIM>(g, um, unit, warp);
             if (!w.valid) continue;
-            const float m = (float)(sh.sum0[w.b] / cells);
+            const float m = MASK ? (sh.sum1[w.b] > 0.0 ? (float)(sh.sum0[w.b] / sh.sum1[w.b]) : 0.f) : (float)(sh.sum0[w.b] / cells);
             for_unit_cells<DIM>(g, a.pf, w, [&](long long off, int nvalid) {
-                for (int j = 0; j < nvalid; ++j) a.x[off + j] -= m;
+                for (int j = 0; j < nvalid; ++j) a.x[off + j] -= MASK ? m * a.acc[off + j] : m;
             });
         }
     }
@@ -273,19 +279,20 @@ k_cg_poisson(CgArgs a)
 
 // ---- host side --------------------------------------------------------------------------------------------------
 
-static int cg_grid_size(int dim, int batch, int* blocks_per_sm_out)
+static const void* cg_kernel(int dim, bool mask)
+{
+    if (dim == 3) return mask ? (const void*)k_cg_poisson<3, true> : (const void*)k_cg_poisson<3, false>;
+    return mask ? (const void*)k_cg_poisson<2, true> : (const void*)k_cg_poisson<2, false>;
+}
+
+static int cg_grid_size(int dim, int batch, bool mask, int* blocks_per_sm_out)
 {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t smem = cg_smem_bytes(batch);
-    if (dim == 3) {
-        cudaFuncSetAttribute(k_cg_poisson<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_poisson<3>, PHI_WARPS_PER_CTA * 32, smem);
-    } else {
-        cudaFuncSetAttribute(k_cg_poisson<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_poisson<2>, PHI_WARPS_PER_CTA * 32, smem);
-    }
+    cudaFuncSetAttribute(cg_kernel(dim, mask), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_kernel(dim, mask), PHI_WARPS_PER_CTA * 32, smem);
     if (blocks_per_sm_out) *blocks_per_sm_out = per_sm;
     return sms * per_sm;
 }
@@ -306,12 +313,14 @@ int phi_launch_cg(const CgLaunch& l, cudaStream_t s)
     const DGrid& g = l.g;
     if (g.batch > CG_MAX_BATCH) { phi_set_error("cg: batch %d exceeds %d (split the batch)", g.batch, CG_MAX_BATCH); return PHI_ERR_UNSUPPORTED; }
     if (l.workspace_bytes < phi_cg_workspace_bytes(g)) { phi_set_error("cg: workspace %zu < %zu bytes", l.workspace_bytes, phi_cg_workspace_bytes(g)); return PHI_ERR_WORKSPACE; }
-    if (phi_ring_enabled()) {
+    const bool mask = l.acc != nullptr;              // obstacles: register-marching kernel (the TMA ring has no mask variant yet)
+    if (phi_ring_enabled() && !mask) {
         const int e = phi_launch_cg_ring(l, nullptr, s);
         if (e != -100) return e;
     }
+    if (mask && l.prm.matrix_offset != 0.f) { phi_set_error("cg: matrix_offset is not supported together with obstacles"); return PHI_ERR_UNSUPPORTED; }
     int per_sm = 0;
-    int grid = cg_grid_size(g.dim, g.batch, &per_sm);
+    int grid = cg_grid_size(g.dim, g.batch, mask, &per_sm);
     if (grid <= 0) { phi_set_error("cg: kernel does not fit on the device (occupancy 0)"); return PHI_ERR_INVALID; }
     const size_t pf_sb = (size_t)g.cext[0] * g.cext[1] * g.cext[2];
     CgArgs a;
@@ -321,7 +330,7 @@ int phi_launch_cg(const CgLaunch& l, cudaStream_t s)
     if (grid > CG_MAX_GRID) grid = CG_MAX_GRID;
     const size_t arr = align_up((size_t)pf_sb * g.batch * sizeof(float), 256);
     unsigned char* ws = (unsigned char*)l.workspace;
-    a.rhs = l.rhs; a.x = l.x;
+    a.rhs = l.rhs; a.x = l.x; a.acc = l.acc;
     if (g.halo != 0) { phi_set_error("cg: z-slab grids need the TMA ring kernel (grid lines too long)"); return PHI_ERR_UNSUPPORTED; }
     a.r = (float*)ws; a.d0 = (float*)(ws + arr); a.d1 = (float*)(ws + 2 * arr);
     a.partials = (double*)(ws + 3 * arr);
@@ -329,8 +338,7 @@ int phi_launch_cg(const CgLaunch& l, cudaStream_t s)
     void* args[] = {&a};
     const size_t smem = cg_smem_bytes(g.batch);
     cudaError_t err;
-    if (g.dim == 3) err = cudaLaunchCooperativeKernel((void*)k_cg_poisson<3>, dim3(grid), dim3(PHI_WARPS_PER_CTA * 32), args, smem, s);
-    else            err = cudaLaunchCooperativeKernel((void*)k_cg_poisson<2>, dim3(grid), dim3(PHI_WARPS_PER_CTA * 32), args, smem, s);
+    err = cudaLaunchCooperativeKernel(cg_kernel(g.dim, mask), dim3(grid), dim3(PHI_WARPS_PER_CTA * 32), args, smem, s);
     if (err != cudaSuccess) { phi_set_error("cg: cooperative launch failed: %s", cudaGetErrorString(err)); return (int)err; }
     return 0;
 }

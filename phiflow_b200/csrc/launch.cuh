@@ -3,8 +3,10 @@
 #include "phi_internal.cuh"
 
 int phi_launch_laplace(const DGrid& g, const DField& f, const float* x, float* y, float coeff, bool axpy, cudaStream_t s);
-int phi_launch_divergence(const DGrid& g, const DVec& v, const DField& cf, float* div, cudaStream_t s);
-int phi_launch_grad_sub(const DGrid& g, const DVec& vin, const DVecOut& v, const DField& pf, const float* p, cudaStream_t s);
+int phi_launch_divergence(const DGrid& g, const DVec& v, const DField& cf, float* div, const float* acc, cudaStream_t s);
+int phi_launch_grad_sub(const DGrid& g, const DVec& vin, const DVecOut& v, const DField& pf, const float* p,
+                        const DField* af, const float* acc, cudaStream_t s);
+int phi_launch_mul_faces(const DGrid& g, const DVec& vin, const DVecOut& v, const float* const mask[3], cudaStream_t s);
 int phi_launch_buoyancy(const DGrid& g, const DVec& vin, const DVecOut& v, const DField& sf, const float* sarr,
                         const float b[3], float dt, cudaStream_t s);
 int phi_launch_axpy(const DGrid& g, const DField& cf, float a, const float* x, float* y, cudaStream_t s);
@@ -20,6 +22,7 @@ struct CgLaunch {
     const float* rhs; float* x;
     PhiCgParams prm; PhiCgResult* result;
     void* workspace; size_t workspace_bytes;
+    const float* acc = nullptr;    // N4: accessible mask
 };
 size_t phi_cg_workspace_bytes(const DGrid& g);
 // TMA ring fast paths (ring_kernels.cu); return -100 when the shape does not fit and the caller must fall back

@@ -188,6 +188,78 @@ __device__ __forceinline__ void phi_march(const DGrid& g, const DField& f, const
     }
 }
 
+// N4: the same march with static obstacles (fluid.masked_laplace, phi/physics/fluid.py:197-202):
+//   q_c = sum_faces min(acc_c, acc_nb) * (v_nb - v_c) / dx^2   for accessible cells (acc_c = 1),   q_c = v_c   inside obstacles.
+// `acc` is the centred accessible mask; its ghost cells follow the value array's rows (periodic: wrapped, zero-gradient:
+// clamped - the flux through such a face is zero anyway because the value ghost equals the centre), except that constant
+// (Dirichlet) ghosts count as accessible (fluid._accessible_extrapolation: BOUNDARY -> ONE).
+template <int DIM, class Src, class Epi>
+__device__ __forceinline__ void phi_march_masked(const DGrid& g, const DField& f, const Src& src, const float* __restrict__ accp,
+                                                 Epi& epi, int b, int xt0, int t, int m0, int m1)
+{
+    const int lane = threadIdx.x & 31;
+    const int x0 = xt0 + lane * 4;
+    const int nx = g.n[0];
+    const bool active = x0 < nx;
+    const int nvalid = active ? min(4, nx - x0) : 0;
+    const float ix2 = g.inv_dx2[0], iy2 = g.inv_dx2[1], iz2 = g.inv_dx2[2];
+    const float im2 = (DIM == 3) ? iz2 : iy2;
+    struct SrcAcc {
+        const float* a;
+        __device__ __forceinline__ float4 load4(long long off) const { return *reinterpret_cast<const float4*>(a + off); }
+        __device__ __forceinline__ float load1(long long off) const { return a[off]; }
+    } sa{accp};
+    DField fa = f;                                   // same rows, but constant ghosts are accessible (1)
+    fa.clo[0] = fa.chi[0] = 1.f;
+    auto rowAt = [&](int tt, int mm) { return DIM == 3 ? phi_row<DIM>(g, f, b, tt, mm) : phi_row<DIM>(g, f, b, mm, 0); };
+    auto accRow = [&](RowRef<DIM> r) { r.cval = 1.f; return phi_load_row4<DIM>(sa, r, x0, active); };
+    auto term = [](float vn, float vc, float an, float ac) { return fminf(an, ac) * (vn - vc); };
+
+    RowRef<DIM> rm = rowAt(t, m0 - 1);
+    float4 vm = phi_load_row4<DIM>(src, rm, x0, active), am = accRow(rm);
+    RowRef<DIM> rc = rowAt(t, m0);
+    float4 vc = phi_load_row4<DIM>(src, rc, x0, active), ac = accRow(rc);
+    for (int m = m0; m < m1; ++m) {
+        const RowRef<DIM> rp = rowAt(t, m + 1);
+        const float4 vp = phi_load_row4<DIM>(src, rp, x0, active), ap = accRow(rp);
+        float4 tl, th, al, ah;
+        if (DIM == 3) {
+            const RowRef<DIM> rl = rowAt(t - 1, m), rh = rowAt(t + 1, m);
+            tl = phi_load_row4<DIM>(src, rl, x0, active); al = accRow(rl);
+            th = phi_load_row4<DIM>(src, rh, x0, active); ah = accRow(rh);
+        }
+        float left = __shfl_up_sync(0xffffffffu, vc.w, 1), aleft = __shfl_up_sync(0xffffffffu, ac.w, 1);
+        float right = __shfl_down_sync(0xffffffffu, vc.x, 1), aright = __shfl_down_sync(0xffffffffu, ac.x, 1);
+        if (active) {
+            if (x0 == 0) { left = phi_ghost_x<DIM>(src, f, rc, false); aleft = phi_ghost_x<DIM>(sa, fa, rc, false); }
+            else if (lane == 0) { left = src.load1(rc.off + x0 - 1); aleft = sa.load1(rc.off + x0 - 1); }
+            if (x0 + 4 >= nx) { right = phi_ghost_x<DIM>(src, f, rc, true); aright = phi_ghost_x<DIM>(sa, fa, rc, true); }
+            else if (lane == 31) { right = src.load1(rc.off + x0 + 4); aright = sa.load1(rc.off + x0 + 4); }
+        }
+        float4 xl = make_float4(left, vc.x, vc.y, vc.z), axl = make_float4(aleft, ac.x, ac.y, ac.z);
+        float4 xr = make_float4(vc.y, vc.z, vc.w, right), axr = make_float4(ac.y, ac.z, ac.w, aright);
+        if (nvalid > 0 && nvalid < 4) { f4_set(xr, nvalid - 1, right); f4_set(axr, nvalid - 1, aright); }
+        float4 q;
+        q.x = (term(xl.x, vc.x, axl.x, ac.x) + term(xr.x, vc.x, axr.x, ac.x)) * ix2 + (term(vm.x, vc.x, am.x, ac.x) + term(vp.x, vc.x, ap.x, ac.x)) * im2;
+        q.y = (term(xl.y, vc.y, axl.y, ac.y) + term(xr.y, vc.y, axr.y, ac.y)) * ix2 + (term(vm.y, vc.y, am.y, ac.y) + term(vp.y, vc.y, ap.y, ac.y)) * im2;
+        q.z = (term(xl.z, vc.z, axl.z, ac.z) + term(xr.z, vc.z, axr.z, ac.z)) * ix2 + (term(vm.z, vc.z, am.z, ac.z) + term(vp.z, vc.z, ap.z, ac.z)) * im2;
+        q.w = (term(xl.w, vc.w, axl.w, ac.w) + term(xr.w, vc.w, axr.w, ac.w)) * ix2 + (term(vm.w, vc.w, am.w, ac.w) + term(vp.w, vc.w, ap.w, ac.w)) * im2;
+        if (DIM == 3) {
+            q.x += (term(tl.x, vc.x, al.x, ac.x) + term(th.x, vc.x, ah.x, ac.x)) * iy2;
+            q.y += (term(tl.y, vc.y, al.y, ac.y) + term(th.y, vc.y, ah.y, ac.y)) * iy2;
+            q.z += (term(tl.z, vc.z, al.z, ac.z) + term(th.z, vc.z, ah.z, ac.z)) * iy2;
+            q.w += (term(tl.w, vc.w, al.w, ac.w) + term(th.w, vc.w, ah.w, ac.w)) * iy2;
+        }
+        if (ac.x == 0.f) q.x = vc.x;
+        if (ac.y == 0.f) q.y = vc.y;
+        if (ac.z == 0.f) q.z = vc.z;
+        if (ac.w == 0.f) q.w = vc.w;
+        if (active) epi(rc.off + x0, vc, q, nvalid);
+        vm = vc; vc = vp; am = ac; ac = ap;
+        rc = rp;
+    }
+}
+
 // Plain array source
 struct SrcArray {
     const float* a;

@@ -904,7 +904,7 @@ int phi_launch_laplace_ring(const DGrid& g, const DField& f, const float* x, flo
 int phi_launch_cg_ring(const CgLaunch& l, const CommDev* cm, cudaStream_t s)
 {
     const DGrid& g = l.g;
-    if (g.batch > CG_MAX_BATCH) return -100;
+    if (g.batch > CG_MAX_BATCH || l.acc) return -100;
     CgRingArgs A;
     const int cgs = (int)((cg_smem_bytes(g.batch) + 127) / 128 * 128);
     const int sms = sm_count();
@@ -927,7 +927,7 @@ int phi_launch_cg_ring(const CgLaunch& l, const CommDev* cm, cudaStream_t s)
     unsigned char* ws = (unsigned char*)l.workspace;
     CgArgs& a = A.a;
     a.g = g; a.pf = l.pf; a.um = UnitMap();
-    a.rhs = l.rhs; a.x = l.x;
+    a.rhs = l.rhs; a.x = l.x; a.acc = nullptr;
     const size_t hoff = (size_t)g.halo * g.cext[0] * g.cext[1];       // pointers address the first owned plane
     a.r = (float*)ws + hoff; a.d0 = (float*)(ws + arr) + hoff; a.d1 = (float*)(ws + 2 * arr) + hoff;
     a.partials = (double*)(ws + 3 * arr);

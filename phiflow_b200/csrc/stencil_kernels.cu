@@ -81,7 +81,7 @@ __device__ __forceinline__ long long phi_off(const DField& f, const Idx& i)
 // A5: div = sum_d (v_d[i + e_d] - v_d[i]) / dx_d over the n_d + 1 faces of the baked field
 template <int DIM>
 __global__ void __launch_bounds__(128)
-k_divergence(DGrid g, DVec v, DField cf, float* __restrict__ div)
+k_divergence(DGrid g, DVec v, DField cf, float* __restrict__ div, const float* __restrict__ accm)
 {
     Idx i;
     if (!phi_thread_index<DIM>(g, i)) return;
@@ -94,13 +94,14 @@ k_divergence(DGrid g, DVec v, DField cf, float* __restrict__ div)
         const float term = __fdiv_rn(hi - lo, g.dx[c]);
         acc = (c == 0) ? term : acc + term;
     }
-    div[phi_off(cf, i)] = acc;
+    const long long o = phi_off(cf, i);
+    div[o] = accm ? acc * accm[o] : acc;
 }
 
 // A6: v_d[face] -= (p[upper cell] - p[lower cell]) / dx_d on the stored faces
 template <int DIM>
 __global__ void __launch_bounds__(128)
-k_grad_sub(DGrid g, DVec vin, DVecOut v, DField pf, const float* __restrict__ p)
+k_grad_sub(DGrid g, DVec vin, DVecOut v, DField pf, const float* __restrict__ p, DField af, const float* __restrict__ accm)
 {
     Idx i;
     if (!phi_thread_index<DIM>(g, i)) return;
@@ -110,7 +111,13 @@ k_grad_sub(DGrid g, DVec vin, DVecOut v, DField pf, const float* __restrict__ p)
         if (!phi_in_range(vin.f[c], DIM, i.x, i.y, i.z)) continue;
         const float up = phi_fetch<DIM>(p, g, pf, i.b, i.x, i.y, i.z);
         const float lw = phi_fetch<DIM>(p, g, pf, i.b, i.x - (c == 0), i.y - (c == 1), i.z - (c == 2));
-        v.p[c][off] = vin.p[c][off] - __fdiv_rn(up - lw, g.dx[c]);
+        float grad = __fdiv_rn(up - lw, g.dx[c]);
+        if (accm) {     // hard_bcs = min of the two adjacent cells' accessibility (fluid.py:134)
+            const float au = phi_fetch<DIM>(accm, g, af, i.b, i.x, i.y, i.z);
+            const float al = phi_fetch<DIM>(accm, g, af, i.b, i.x - (c == 0), i.y - (c == 1), i.z - (c == 2));
+            grad *= fminf(au, al);
+        }
+        v.p[c][off] = vin.p[c][off] - grad;
     }
 }
 
@@ -134,6 +141,22 @@ k_buoyancy(DGrid g, DVec vin, DVecOut v, DField sf, const float* __restrict__ s,
     }
 }
 
+// N4: apply_boundary_conditions for stationary obstacles: v_c *= mask_c on the stored faces (fluid.py:212-240)
+template <int DIM>
+__global__ void __launch_bounds__(128)
+k_mul_faces(DGrid g, DVec vin, DVecOut v, const float* m0, const float* m1, const float* m2)
+{
+    Idx i;
+    if (!phi_thread_index<DIM>(g, i)) return;
+    const long long off = phi_off(vin.f[0], i);
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) {
+        if (!phi_in_range(vin.f[c], DIM, i.x, i.y, i.z)) continue;
+        const float* m = c == 0 ? m0 : (c == 1 ? m1 : m2);
+        v.p[c][off] = vin.p[c][off] * m[off];
+    }
+}
+
 template <int DIM>
 __global__ void __launch_bounds__(128)
 k_axpy(DGrid g, DField cf, float a, const float* __restrict__ x, float* __restrict__ y)
@@ -150,17 +173,19 @@ static dim3 scalar_grid(const DGrid& g)
     return dim3((g.fext[0] + 127) / 128, g.fext[1], g.fext[2] * g.batch);
 }
 
-int phi_launch_divergence(const DGrid& g, const DVec& v, const DField& cf, float* div, cudaStream_t s)
+int phi_launch_divergence(const DGrid& g, const DVec& v, const DField& cf, float* div, const float* acc, cudaStream_t s)
 {
-    if (g.dim == 3) k_divergence<3><<<scalar_grid(g), 128, 0, s>>>(g, v, cf, div);
-    else            k_divergence<2><<<scalar_grid(g), 128, 0, s>>>(g, v, cf, div);
+    if (g.dim == 3) k_divergence<3><<<scalar_grid(g), 128, 0, s>>>(g, v, cf, div, acc);
+    else            k_divergence<2><<<scalar_grid(g), 128, 0, s>>>(g, v, cf, div, acc);
     return (int)cudaGetLastError();
 }
 
-int phi_launch_grad_sub(const DGrid& g, const DVec& vin, const DVecOut& v, const DField& pf, const float* p, cudaStream_t s)
+int phi_launch_grad_sub(const DGrid& g, const DVec& vin, const DVecOut& v, const DField& pf, const float* p,
+                        const DField* af, const float* acc, cudaStream_t s)
 {
-    if (g.dim == 3) k_grad_sub<3><<<scalar_grid(g), 128, 0, s>>>(g, vin, v, pf, p);
-    else            k_grad_sub<2><<<scalar_grid(g), 128, 0, s>>>(g, vin, v, pf, p);
+    const DField a = af ? *af : pf;
+    if (g.dim == 3) k_grad_sub<3><<<scalar_grid(g), 128, 0, s>>>(g, vin, v, pf, p, a, acc);
+    else            k_grad_sub<2><<<scalar_grid(g), 128, 0, s>>>(g, vin, v, pf, p, a, acc);
     return (int)cudaGetLastError();
 }
 
@@ -169,6 +194,13 @@ int phi_launch_buoyancy(const DGrid& g, const DVec& vin, const DVecOut& v, const
 {
     if (g.dim == 3) k_buoyancy<3><<<scalar_grid(g), 128, 0, s>>>(g, vin, v, sf, sarr, b[0], b[1], b[2], dt);
     else            k_buoyancy<2><<<scalar_grid(g), 128, 0, s>>>(g, vin, v, sf, sarr, b[0], b[1], 0.f, dt);
+    return (int)cudaGetLastError();
+}
+
+int phi_launch_mul_faces(const DGrid& g, const DVec& vin, const DVecOut& v, const float* const mask[3], cudaStream_t s)
+{
+    if (g.dim == 3) k_mul_faces<3><<<scalar_grid(g), 128, 0, s>>>(g, vin, v, mask[0], mask[1], mask[2]);
+    else            k_mul_faces<2><<<scalar_grid(g), 128, 0, s>>>(g, vin, v, mask[0], mask[1], nullptr);
     return (int)cudaGetLastError();
 }
 

@@ -126,6 +126,15 @@ class Box:
             ok &= (pts[..., i] >= self.lower[k]) & (pts[..., i] <= self.upper[k])
         return ok
 
+    def signed_distance(self, pts):
+        """Box.approximate_signed_distance (phi/geom/_box.py:217-236): signed L-infinity distance to the nearest side."""
+        d = None
+        for i, k in enumerate(self.names):
+            c, h = 0.5 * (self.lower[k] + self.upper[k]), 0.5 * (self.upper[k] - self.lower[k])
+            di = np.abs(pts[..., i] - np.float32(c)) - np.float32(h)
+            d = di if d is None else np.maximum(d, di)
+        return d.astype(np.float32)
+
 
 class Sphere:
     """Sphere(x=50, y=9.5, radius=5)  (phi/geom/_sphere.py)."""
@@ -135,6 +144,11 @@ class Sphere:
 
     def lies_inside(self, pts):
         return np.sum((pts - np.asarray(self.center, np.float32)) ** 2, -1) <= self.radius ** 2
+
+    def signed_distance(self, pts):
+        """Sphere.approximate_signed_distance (phi/geom/_sphere.py:107-120)."""
+        d = np.sqrt(np.maximum(np.sum((pts - np.asarray(self.center, np.float32)) ** 2, -1, dtype=np.float32), np.float32(1e-6)))
+        return (d - np.float32(self.radius)).astype(np.float32)
 
     def soft_mask(self, pts, cell_radius):
         """Geometry.approximate_fraction_inside (phi/geom/_geom.py:278-308) with Sphere.approximate_signed_distance
@@ -527,11 +541,44 @@ def _finish_solve(dom, solve: Solve):
     return info
 
 
+def _obstacle_masks(velocity: StaggeredGrid, obstacles):
+    """Static obstacles (phi/physics/fluid.py:130-137, 212-240): returns (accessible centred mask, per-component face factors
+    1 - resample(geometry, velocity, soft=True, balance=1)).  Geometry sampling is set-up work done on the host."""
+    geoms = list(obstacles) if isinstance(obstacles, (tuple, list)) else [obstacles]
+    _require(all(isinstance(o, (Box, Sphere)) for o in geoms), "obstacles other than stationary Box / Sphere geometries")
+    centred = CenteredGrid(0, ZERO, velocity.bounds, velocity.batch, **dict(zip(velocity.axes, velocity.res)))
+    pts = centred.points()
+    inside = np.zeros(pts.shape[:-1], bool)
+    for o in geoms:
+        inside |= o.lies_inside(pts)
+    accessible = velocity.dom.centered_from_numpy((~inside).astype(np.float32))
+    radius = np.float32(np.sqrt(sum((h * 0.5) ** 2 for h in velocity.dx)))        # bounding radius of a (staggered) cell
+    factors = []
+    for c in range(len(velocity.res)):
+        fpts = velocity.face_points(c)
+        f = np.ones(fpts.shape[:-1], np.float32)
+        for o in geoms:                                                          # approximate_fraction_inside, balance = 1
+            f *= np.float32(1) - np.clip(np.float32(1) - o.signed_distance(fpts) / radius, 0, 1).astype(np.float32)
+        factors.append(f)
+    return accessible, velocity.dom.faces_from_numpy(factors, velocity.vspec)
+
+
 def make_incompressible(velocity: StaggeredGrid, obstacles=(), solve: Solve = None, active=None, order=2):
-    """fluid.make_incompressible (phi/physics/fluid.py:94-162): returns (divergence-free velocity, pressure)."""
+    """fluid.make_incompressible (phi/physics/fluid.py:94-162): returns (divergence-free velocity, pressure).
+    obstacles: stationary Box / Sphere geometries (row N4)."""
     solve = solve or Solve()
     _require(isinstance(velocity, StaggeredGrid), "CenteredGrid velocities")
-    _require(not obstacles and active is None and order == 2, "obstacles / active masks / higher order")
+    _require(active is None and order == 2, "active masks / higher order")
+    if obstacles:
+        accessible, factors = _obstacle_masks(velocity, obstacles)
+        res = dict(zip(velocity.axes, velocity.res))
+        p_data = solve.x0.data.clone() if solve.x0 is not None else velocity.dom.alloc_centered()
+        v_data = [c.clone() for c in velocity.data]
+        ops.mul_faces(velocity.dom, velocity.vspec, v_data, factors)             # apply_boundary_conditions
+        ops.make_incompressible(velocity.dom, velocity.vspec, v_data, p_data, _cg_params(velocity, solve), accessible=accessible)
+        _finish_solve(velocity.dom, solve)
+        pressure = CenteredGrid(boundary=_pressure_boundary(velocity.boundary), bounds=velocity.bounds, batch=velocity.batch, _data=p_data, **res)
+        return velocity.with_values(v_data), pressure
     res = dict(zip(velocity.axes, velocity.res))
     if solve.x0 is not None:
         _require(isinstance(solve.x0, CenteredGrid) and solve.x0.res == velocity.res, "x0 on a different grid")

@@ -419,3 +419,45 @@ def test_config_c3_taylor_green_3d():
         np.testing.assert_allclose(got[c], v[c], rtol=0, atol=2e-4)
     assert all(b <= a * (1 + 1e-6) for a, b in zip(energy, energy[1:]))
     assert abs(energy[-1] / energy[0] - 1) < 0.05
+
+
+@pytest.mark.parametrize('vname', ['zero', 'open', 'periodic', 'mixed', 'zero3', 'periodic3', 'wall_open3'])
+@pytest.mark.parametrize('big', [False, True])
+def test_make_incompressible_with_obstacle(vname, big):
+    """SURVEY N4 (phi/physics/fluid.py:121-162 with obstacles): masked divergence, masked CG, masked gradient vs the oracle
+    (whose masked matrix is pinned against the reference's traced matrix in tests/test_oracle_golden.py)."""
+    vbc = ALL_V[vname]
+    d = len(vbc)
+    rng = np.random.default_rng(11)
+    if big:
+        res = (128, 20) if d == 2 else (128, 12, 8)
+    else:
+        res = (14, 11) if d == 2 else (10, 8, 7)
+    dx = tuple(50.0 / r for r in res)
+    acc = np.ones(res, np.float32)
+    if d == 2:
+        acc[res[0] // 3:res[0] // 2, 2:6] = 0
+        acc[0:2, res[1] - 3:] = 0                        # an obstacle touching the domain boundary
+    else:
+        acc[res[0] // 3:res[0] // 2, 2:5, 1:4] = 0
+    hard = O.hard_bcs_faces(acc, vbc)
+    v = [c * np.float32(0.1) for c in rand_staggered(rng, res, vbc)]
+    vmask = [h.copy() for h in hard]                     # any face factor works for the test; use the hard mask itself
+    dom = ops.Domain(res, dx, 1, vbc=vbc)
+    dv = dom.faces_from_numpy(v, vbc)
+    ops.mul_faces(dom, vbc, dv, dom.faces_from_numpy(vmask, vbc))
+    dacc = dom.centered_from_numpy(acc)
+    prm = ops.cg_params(vbc, rtol=1e-5, atol=1e-6)
+    dv, dp = ops.make_incompressible(dom, vbc, dv, None, prm, accessible=dacc)
+    info = ops.read_results(dom)
+    assert info['converged'][0] == 1 and info['diverged'][0] == 0
+    v_ref, p_ref, inf = O.make_incompressible_obstacles(v, vbc, res, dx, acc, vmask, rtol=1e-5, atol=1e-6)
+    assert abs(int(info['iterations'][0]) - inf['iterations']) <= max(3, inf['iterations'] // 8), (info['iterations'], inf['iterations'])
+    got = dom.faces_to_numpy(dv, vbc)
+    for c in range(d):
+        np.testing.assert_allclose(got[c], v_ref[c], rtol=0, atol=2e-4 * max(np.abs(v[c]).max(), 1e-3))
+    p = dom.centered_to_numpy(dp)
+    assert np.abs(p[acc == 0]).max() == 0.0                                   # pressure stays zero inside obstacles
+    div = dom.centered_to_numpy(ops.divergence(dom, vbc, dv)) * acc
+    vscale = max(np.abs(c).max() for c in v) * sum(2.0 / h for h in dx)
+    assert np.abs(div).max() < 2e-4 * vscale
