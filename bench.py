@@ -206,7 +206,7 @@ def run_ours(args):
                        "cg_iterations_per_step": float(np.mean(iters)), "cg_ms_per_step": float(np.mean(cg_ms)),
                        "l2": "inputs (512 MiB per array) exceed L2, no flush"},
             "clocks": clocks, "gpu_launches": sim.launches_per_step * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "k_cg_poisson<3>", "achieved": cg_gbs, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_cg_ring<3,false> (persistent CG solve)", "achieved": cg_gbs, "peak": peak, "unit": "GB/s",
                          "frac": cg_gbs / peak, "traffic": None, "peak_kind": peak_kind,
                          "algorithmic_bytes": "cells*(32*iterations+32) per solve"},
             "laplace": {"achieved": lap_gbs, "peak": peak, "frac": lap_gbs / peak, "unit": "GB/s", "ms": lap_ms,
