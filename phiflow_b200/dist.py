@@ -32,6 +32,19 @@ def local_bc(spec, rank: int, world: int):
     return (spec[0], spec[1], (zlo, zhi))
 
 
+def batch_shard(total_batch: int, rank: int = None, world: int = None):
+    """Batched 2-D runs (BASELINE configs[4]) shard the batch axis: returns (first entry, count) of this rank.
+    Batch entries are independent systems (PhiML/phiml/backend/_linalg.py:72-87), so the sharded run needs NO collective;
+    ranks only meet at the final timing barrier."""
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    base, rem = divmod(int(total_batch), int(world))
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)
+
+
 class Slab:
     """Geometry + communication of one rank's z-slab."""
 

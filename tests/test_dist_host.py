@@ -86,6 +86,17 @@ def test_slab_halo_exchange_gloo(world, periodic):
         assert msg == 'ok', f"rank {rank}: {msg}"
 
 
+def test_batch_shard_covers_every_entry_once():
+    """BASELINE configs[4]: batch=512 over 8 ranks -> 64 each; ragged batches are spread over the first ranks."""
+    from phiflow_b200.dist import batch_shard
+    assert [batch_shard(512, r, 8) for r in range(8)] == [(64 * r, 64) for r in range(8)]
+    parts = [batch_shard(13, r, 4) for r in range(4)]
+    assert parts == [(0, 4), (4, 3), (7, 3), (10, 3)]
+    covered = [i for first, n in parts for i in range(first, first + n)]
+    assert covered == list(range(13))
+    assert batch_shard(5, 0, 1) == (0, 5)
+
+
 def test_local_bc_single_rank_is_identity():
     from phiflow_b200.dist import local_bc
     spec = (('periodic', 'periodic'), (0.0, 'zg'), ('zg', 0.0))

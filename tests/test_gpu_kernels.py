@@ -461,3 +461,45 @@ def test_make_incompressible_with_obstacle(vname, big):
     div = dom.centered_to_numpy(ops.divergence(dom, vbc, dv)) * acc
     vscale = max(np.abs(c).max() for c in v) * sum(2.0 / h for h in dx)
     assert np.abs(div).max() < 2e-4 * vscale
+
+
+def test_config_c5_kolmogorov_batched_2d():
+    """BASELINE configs[4] at 8 x 32^2: batched 2-D periodic Kolmogorov flow (forcing sin(4y) on the x component,
+    examples/grids/Higher_order_Kolmogorov.ipynb:83-84, here with the order-2 operator-split step of SURVEY 8d):
+    every batch entry is an independent system and must match its own un-batched oracle run."""
+    n, batch = 32, 8
+    res = (n, n)
+    L = 2 * np.pi
+    dx = (L / n, L / n)
+    lower, upper = (0.0, 0.0), (L, L)
+    vbc = O.uniform_bc(2, 'periodic')
+    fbc = O.uniform_bc(2, 'periodic')
+    yc = (np.arange(n) + 0.5) * dx[1]
+    forcing = np.broadcast_to(np.sin(4 * yc)[None, :], res).astype(np.float32)
+    v0 = [np.stack([(0.01 * np.random.default_rng(100 + b).standard_normal(res)).astype(np.float32) for b in range(batch)]) for _ in range(2)]
+    dom = ops.Domain(res, dx, batch, vbc=vbc)
+    dv = dom.faces_from_numpy(v0, vbc)
+    dforce = dom.centered_from_numpy(forcing)
+    dp = dom.alloc_centered()
+    prm = ops.cg_params(vbc, rtol=1e-4, atol=1e-6)
+    dt = 0.05
+    A = O.poisson_matrix(res, dx, O.pressure_bc(vbc))
+    v = [[v0[0][b], v0[1][b]] for b in range(batch)]
+    p = [np.zeros(res, np.float32) for _ in range(batch)]
+    for _ in range(3):
+        dv2 = ops.advect_staggered(dom, vbc, dv, vbc, dv, dt)
+        ops.add_buoyancy(dom, vbc, fbc, dforce, (1.0, 0.0), dt, dv2)
+        dv, dp = ops.make_incompressible(dom, vbc, dv2, dp, prm)
+        assert ops.read_results(dom)['converged'].all()
+        for b in range(batch):
+            vb = O.semi_lagrangian_staggered(v[b], vbc, v[b], vbc, res, lower, upper, dt)
+            faces = O.centered_to_faces(forcing * np.float32(1.0), fbc, vbc)
+            vb = [vb[0] + faces[0] * np.float32(dt), vb[1]]
+            vb, p[b], info = O.make_incompressible(vb, vbc, res, dx, rtol=1e-4, atol=1e-6, x0=p[b], use_matrix_offset=False, matrix=A)
+            v[b] = vb
+    got = dom.faces_to_numpy(dv, vbc, squeeze=False)
+    for b in range(batch):
+        for c in range(2):
+            np.testing.assert_allclose(got[c][b], v[b][c], rtol=0, atol=5e-5)
+    its = ops.read_results(dom)['iterations']
+    assert its.min() >= 1 and len(set(its.tolist())) >= 1
