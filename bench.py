@@ -66,7 +66,7 @@ def cpu_sample(n: int, steps: int, warmup: int, full: int):
     el = time.perf_counter() - t0
     sample_sps = steps / el
     return {"value": sample_sps * (n ** 3) / float(full ** 3), "unit": "steps/s", "cores": 1, "kind": "port",
-            "sample": f"{steps} steps of the same plume at {n}^3 (1/{(full // n) ** 3} of the cells), NumPy/SciPy oracle port, "
+            "sample": f"{steps} steps of the same plume at {n}^3 (1/{(full / n) ** 3:.1f} of the cells), NumPy/SciPy oracle port, "
                       f"{sample_sps:.4f} steps/s measured, scaled by cells; CG iterations/step {np.mean(iters):.1f}; "
                       f"the reference's NumPy path is single-threaded ({os.cpu_count()} cores present)"}
 
@@ -198,7 +198,7 @@ def run_ours(args):
     # transposes to the device layout, steps, transposes back and downloads it
     e2e = run_e2e(sim, args, torch)
 
-    base = cpu_sample(args.cpu_size, 2, 1, n) if not args.no_cpu else None
+    base = cpu_sample(args.cpu_size, 3, 1, n) if not args.no_cpu else None
     line = {"metric": METRIC, "value": 1e3 / ms, "unit": "steps/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
@@ -257,7 +257,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--size', type=int, default=512)
-    ap.add_argument('--cpu-size', type=int, default=64, dest='cpu_size')
+    ap.add_argument('--cpu-size', type=int, default=96, dest='cpu_size')
     ap.add_argument('--no-cpu', action='store_true', dest='no_cpu')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != 'reference' else args.warmup
