@@ -58,7 +58,6 @@ __device__ __forceinline__ float phi_velocity_at(const DGrid& g, const DVec& vel
     }
 }
 
-#define ADVECT_ROWS 8
 struct Lookup { int i[3]; float t[3]; };    // base neighbour index and interpolation weight per axis
 
 template <int DIM>
@@ -150,22 +149,10 @@ __global__ void __launch_bounds__(128)
 k_advect(DGrid g, DVec vel, DField ff, int target, const float* __restrict__ src, float* __restrict__ dst, float dt)
 {
     int b, x, y, z;
-    // one CTA covers 128 samples in x and ADVECT_ROWS grid lines (fewer, longer-lived CTAs: 1M tiny CTAs at 512^3 were
-    // dominated by block scheduling)
-    x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int zb = blockIdx.z;
-    if (DIM == 3) { z = zb % g.fext[2]; b = zb / g.fext[2]; } else { z = 0; b = zb; }
-    if (x > ff.hi[0] || x < ff.lo[0]) return;
-    if (DIM == 3 && (z > ff.hi[2] || z < ff.lo[2])) return;
-    const int y0 = blockIdx.y * ADVECT_ROWS;
-#pragma unroll 2
-    for (int r_ = 0; r_ < ADVECT_ROWS; ++r_) {
-        y = y0 + r_;
-        if (y > ff.hi[1] || y < ff.lo[1]) continue;
-        const Lookup L = phi_lookup<DIM>(g, vel, target, b, x, y, z, dt);
-        const float r = phi_interp<DIM, false>(src, g, ff, b, L, nullptr, nullptr);
-        dst[(long long)b * ff.sb + (long long)z * ff.sz + (long long)y * ff.sy + x] = r;
-    }
+    if (!advect_index<DIM>(g, ff, b, x, y, z)) return;
+    const Lookup L = phi_lookup<DIM>(g, vel, target, b, x, y, z, dt);
+    const float r = phi_interp<DIM, false>(src, g, ff, b, L, nullptr, nullptr);
+    dst[(long long)b * ff.sb + (long long)z * ff.sz + (long long)y * ff.sy + x] = r;
 }
 
 // MacCormack (advect.py:182-215) = three passes over proven building blocks:
@@ -195,9 +182,8 @@ static dim3 scalar_grid(const DGrid& g)
 int phi_launch_advect(const DGrid& g, const DVec& vel, const DField& ff, int target_comp, const float* src, float* dst,
                       float dt, cudaStream_t s)
 {
-    const dim3 grid((g.fext[0] + 127) / 128, (g.fext[1] + ADVECT_ROWS - 1) / ADVECT_ROWS, g.fext[2] * g.batch);
-    if (g.dim == 3) k_advect<3><<<grid, 128, 0, s>>>(g, vel, ff, target_comp, src, dst, dt);
-    else            k_advect<2><<<grid, 128, 0, s>>>(g, vel, ff, target_comp, src, dst, dt);
+    if (g.dim == 3) k_advect<3><<<scalar_grid(g), 128, 0, s>>>(g, vel, ff, target_comp, src, dst, dt);
+    else            k_advect<2><<<scalar_grid(g), 128, 0, s>>>(g, vel, ff, target_comp, src, dst, dt);
     return (int)cudaGetLastError();
 }
 
