@@ -35,6 +35,7 @@ struct RingCfg {
     int units_per_batch, total_units;
     int groups;                // ceil(TY * nx4 / 256)
     int shfl_ok;               // lanes of a warp own consecutive groups of one line -> x neighbours via shuffles
+    int hint;                  // 1: element-wise lines are fetched with an L2 evict-first policy
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
@@ -61,6 +62,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// same copy with an L2 evict-first policy: element-wise streams (x, r, rhs) are read once per pass, so they should not push the
+// halo lines that neighbouring CTAs still need out of L2
+__device__ __forceinline__ void bulk_g2s_stream(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
@@ -165,7 +175,10 @@ __device__ __forceinline__ void ring_produce(Ring& rg, const RingCfg& cfg, const
     __syncwarp();
 #pragma unroll
     for (int it = 0; it < 4; ++it)
-        if (mask & (1u << it)) bulk_g2s(sbase + pu.dsto[it], pu.base[it] + pu.yoff[it] + zoff, row_bytes, full);
+        if (mask & (1u << it)) {
+            if (cfg.hint && (pu.emask & (1u << it))) bulk_g2s_stream(sbase + pu.dsto[it], pu.base[it] + pu.yoff[it] + zoff, row_bytes, full);
+            else bulk_g2s(sbase + pu.dsto[it], pu.base[it] + pu.yoff[it] + zoff, row_bytes, full);
+        }
     rg.pos.next(cfg.R);
 }
 
@@ -829,6 +842,7 @@ static bool ring_config(const DGrid& g, int lines_a, int lines_b, int reserve_by
     while (g.dim == 2 && c.TY > 1 && c.TY / 2 >= g.n[1]) c.TY /= 2;
     c.groups = (c.TY * c.nx4 + RING_CONSUMERS - 1) / RING_CONSUMERS;
     c.shfl_ok = (c.nx4 % 32 == 0) ? 1 : 0;
+    { const char* e = getenv("PHICUDA_RING_HINT"); c.hint = (e && e[0] == '1') ? 1 : 0; }
     if (g.dim == 3) {
         c.nyt = (g.n[1] + c.TY - 1) / c.TY;
         // z chunking: every unit pays a pipeline refill + two halo planes (~ (ZC+2)/ZC), and the persistent grid of
