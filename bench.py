@@ -36,6 +36,16 @@ def load_peaks():
     return 6650.0, 'fallback'
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the CG kernel in this bench (ncu --set full capture of the
+    same command, committed as profiles/r1_cg_traffic.json); None when no capture is committed."""
+    path = os.path.join(ROOT, 'profiles', 'r1_cg_traffic.json')
+    try:
+        return float(json.load(open(path))['dram_bytes_per_launch'])
+    except Exception:
+        return None
+
+
 from phiflow_b200._clocks import ClockSampler  # noqa: E402
 
 
@@ -207,7 +217,7 @@ def run_ours(args):
                        "l2": "inputs (512 MiB per array) exceed L2, no flush"},
             "clocks": clocks, "gpu_launches": sim.launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "kernel": "k_cg_ring<3,false> (persistent CG solve)", "achieved": cg_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": cg_gbs / peak, "traffic": None, "peak_kind": peak_kind,
+                         "frac": cg_gbs / peak, "traffic": load_traffic(), "peak_kind": peak_kind,
                          "algorithmic_bytes": "cells*(32*iterations+32) per solve"},
             "laplace": {"achieved": lap_gbs, "peak": peak, "frac": lap_gbs / peak, "unit": "GB/s", "ms": lap_ms,
                         "algorithmic_bytes": "8 B/cell"},
