@@ -15,11 +15,12 @@ struct CgArgs {
 };
 
 struct CgShared {                   // per-thread view of the CTA's shared memory (pointers carved from one dynamic block)
-    double (*warp_acc)[16];   // [2][warps] (up to 16 warps per CTA)
+    double (*warp_acc)[32];   // [2][warps] (up to 32 warps per CTA)
     double* sum0;                  // reduced accumulator 0 per batch entry
     double* sum1;
     double* delta;
     float* alpha;
+    float* aprev;                  // alpha of the previous iteration (deferred x update of the ring kernel)
     float* beta;
     float* offs;                   // c * S  (offset part of q)
     float* mean;
@@ -33,7 +34,7 @@ struct CgShared {                   // per-thread view of the CTA's shared memor
 __host__ __device__ inline size_t cg_smem_bytes(int batch)
 {
     const size_t b8 = ((size_t)batch + 1) / 2 * 2;      // keep 8-byte alignment of what follows
-    return 2 * 16 * sizeof(double) + 3 * b8 * sizeof(double) + 6 * b8 * sizeof(float)
+    return 2 * 32 * sizeof(double) + 3 * b8 * sizeof(double) + 7 * b8 * sizeof(float)
          + (b8 + 2) * sizeof(int) + 3 * (b8 + 16);
 }
 
@@ -42,11 +43,12 @@ __device__ __forceinline__ CgShared cg_carve(unsigned char* base, int batch)
     const size_t b8 = ((size_t)batch + 1) / 2 * 2;
     CgShared sh;
     unsigned char* p = base;
-    sh.warp_acc = reinterpret_cast<double (*)[16]>(p); p += 2 * 16 * sizeof(double);
+    sh.warp_acc = reinterpret_cast<double (*)[32]>(p); p += 2 * 32 * sizeof(double);
     sh.sum0 = (double*)p; p += b8 * sizeof(double);
     sh.sum1 = (double*)p; p += b8 * sizeof(double);
     sh.delta = (double*)p; p += b8 * sizeof(double);
     sh.alpha = (float*)p; p += b8 * sizeof(float);
+    sh.aprev = (float*)p; p += b8 * sizeof(float);
     sh.beta = (float*)p; p += b8 * sizeof(float);
     sh.offs = (float*)p; p += b8 * sizeof(float);
     sh.mean = (float*)p; p += b8 * sizeof(float);

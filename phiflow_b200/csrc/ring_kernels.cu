@@ -33,9 +33,12 @@ struct RingCfg {
     int stage_floats;          // floats between consecutive stages
     int ZC, nyt, nzc;
     int units_per_batch, total_units;
-    int groups;                // ceil(TY * nx4 / 256)
+    int consumers;             // consumer threads per CTA (256 or 512); the producer warp follows them
+    int groups;                // ceil(TY * nx4 / consumers)
     int shfl_ok;               // lanes of a warp own consecutive groups of one line -> x neighbours via shuffles
     int hint;                  // 1: element-wise lines are fetched with an L2 evict-first policy
+    int merge;                 // 1: lines that are contiguous in memory travel in one bulk copy
+    int dbg;                   // profiling only (PHICUDA_RING_DEBUG): 1 skip CG pass A, 2 skip pass B, 4 consumers skip the arithmetic
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
@@ -98,7 +101,7 @@ __device__ __forceinline__ void ring_init(Ring& rg, unsigned char* smem, const R
     if (threadIdx.x == 0) {
         for (int s = 0; s < cfg.R; ++s) {
             mbar_init(rg.full0 + 8 * s, 1);
-            mbar_init(rg.empty0 + 8 * s, RING_CONSUMERS / 32);
+            mbar_init(rg.empty0 + 8 * s, cfg.consumers / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -113,6 +116,7 @@ struct ProdUnit {
     long long yoff[4];          // b*sb + y*sy of the source line (boundary already applied to y)
     const float* base[4];       // source array
     uint32_t dsto[4];           // byte offset of the destination line inside a stage
+    uint32_t nbytes[4];         // bytes of the copy this lane issues: consecutive lines of one array are merged into one copy
     unsigned hmask, emask;      // which of the 4 lines are active haloed / element-wise lines
     int tot_h, tot_e;           // warp totals of active lines
 };
@@ -123,12 +127,16 @@ __device__ __forceinline__ void prod_unit_setup(ProdUnit& pu, const RingCfg& cfg
                                                 int b, int y0)
 {
     const int lane = threadIdx.x & 31, hrows = cfg.TY + 2;
+    const uint32_t row_bytes = (uint32_t)cfg.pitch * 4u;
+    const bool mergeable = cfg.merge && pf.sy == cfg.pitch;      // neighbouring lines are contiguous in memory and in the stage
     pu.hmask = pu.emask = 0;
     int ch = 0, ce = 0;
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
         const int r = lane + 32 * it;
-        pu.yoff[it] = 0; pu.base[it] = nullptr; pu.dsto[it] = 0;
+        pu.yoff[it] = 0; pu.base[it] = nullptr; pu.dsto[it] = 0; pu.nbytes[it] = row_bytes;
+        int key = -1, yv = 0;                                    // array of an active line, its source row
+        bool halo_line = false;
         if (r < NHslots * hrows) {
             const int arr = r / hrows, j = r - arr * hrows;
             int yy = y0 - 1 + j; float cv;
@@ -136,7 +144,7 @@ __device__ __forceinline__ void prod_unit_setup(ProdUnit& pu, const RingCfg& cfg
                 pu.yoff[it] = (long long)b * pf.sb + (long long)yy * pf.sy;
                 pu.base[it] = hsrc[arr];
                 pu.dsto[it] = 4u * (uint32_t)((arr * hrows + j) * cfg.pitch);
-                pu.hmask |= 1u << it; ch++;
+                key = arr; yv = yy; halo_line = true; ch++;
             }
         } else if (r < NHslots * hrows + NE * cfg.TY) {
             const int q = r - NHslots * hrows, arr = q / cfg.TY, j = q - arr * cfg.TY;
@@ -145,8 +153,17 @@ __device__ __forceinline__ void prod_unit_setup(ProdUnit& pu, const RingCfg& cfg
                 pu.yoff[it] = (long long)b * pf.sb + (long long)yy * pf.sy;
                 pu.base[it] = esrc[arr];
                 pu.dsto[it] = 4u * (uint32_t)((NHslots * hrows + arr * cfg.TY + j) * cfg.pitch);
-                pu.emask |= 1u << it; ce++;
+                key = 8 + arr; yv = yy; ce++;
             }
+        }
+        // a line that continues the one held by the previous lane (same array, next row) rides on that lane's copy
+        const int pkey = __shfl_up_sync(0xffffffffu, key, 1), pyv = __shfl_up_sync(0xffffffffu, yv, 1);
+        const bool cont = mergeable && key >= 0 && lane > 0 && pkey == key && pyv + 1 == yv;
+        const unsigned cm = __ballot_sync(0xffffffffu, cont);
+        if (key >= 0 && !cont) {
+            const unsigned follow = lane == 31 ? 0u : (cm >> (lane + 1));
+            pu.nbytes[it] = (uint32_t)__ffs(~follow) * row_bytes;          // 1 + number of lines that continue this one
+            if (halo_line) pu.hmask |= 1u << it; else pu.emask |= 1u << it;
         }
     }
 #pragma unroll
@@ -176,8 +193,8 @@ __device__ __forceinline__ void ring_produce(Ring& rg, const RingCfg& cfg, const
 #pragma unroll
     for (int it = 0; it < 4; ++it)
         if (mask & (1u << it)) {
-            if (cfg.hint && (pu.emask & (1u << it))) bulk_g2s_stream(sbase + pu.dsto[it], pu.base[it] + pu.yoff[it] + zoff, row_bytes, full);
-            else bulk_g2s(sbase + pu.dsto[it], pu.base[it] + pu.yoff[it] + zoff, row_bytes, full);
+            if (cfg.hint && (pu.emask & (1u << it))) bulk_g2s_stream(sbase + pu.dsto[it], pu.base[it] + pu.yoff[it] + zoff, pu.nbytes[it], full);
+            else bulk_g2s(sbase + pu.dsto[it], pu.base[it] + pu.yoff[it] + zoff, pu.nbytes[it], full);
         }
     rg.pos.next(cfg.R);
 }
@@ -215,7 +232,7 @@ __device__ __forceinline__ void groups_init(ThreadGroups& tg, const RingCfg& cfg
     tg.needl = tg.needr = 0;
 #pragma unroll
     for (int k = 0; k < RING_G; ++k) {
-        const int gi = threadIdx.x + k * RING_CONSUMERS;
+        const int gi = threadIdx.x + k * cfg.consumers;
         const int j = gi / cfg.nx4, x0 = (gi - j * cfg.nx4) * 4;
         tg.j[k] = (k < cfg.groups && j < cfg.TY && x0 < nx) ? j : -1;
         tg.soff[k] = (j + 1) * cfg.pitch + x0;
@@ -228,8 +245,11 @@ __device__ __forceinline__ void groups_init(ThreadGroups& tg, const RingCfg& cfg
         if (lane == 31) tg.needr |= 1u << k;
         if (x0 == 0) { tg.needl |= 1u << k; tg.xlo[k] = pf.klo[0] == PHI_BC_PERIODIC ? row + nx - 1 : row; }
         if (x0 + 4 >= nx) { tg.needr |= 1u << k; tg.xro[k] = pf.khi[0] == PHI_BC_PERIODIC ? row : row + nx - 1; }
+        // lanes that take their neighbour from a shuffle still execute the (branch-free) edge load: one broadcast address
+        if (!(tg.needl & (1u << k))) tg.xlo[k] = 0;
+        if (!(tg.needr & (1u << k))) tg.xro[k] = 0;
     }
-    tg.fast_ok = cfg.shfl_ok && (cfg.nx4 * 4 == nx) && (cfg.TY * cfg.nx4 == cfg.groups * RING_CONSUMERS)
+    tg.fast_ok = cfg.shfl_ok && (cfg.nx4 * 4 == nx) && (cfg.TY * cfg.nx4 == cfg.groups * cfg.consumers)
                  && pf.klo[0] != PHI_BC_CONST && pf.khi[0] != PHI_BC_CONST;
 }
 
@@ -330,19 +350,24 @@ __device__ __forceinline__ void ring_compute(const RingCfg& cfg, const DGrid& g,
             q.z += (zm.z + zp.z - 2.f * c.z) * iz2;
             q.w += (zm.w + zp.w - 2.f * c.w) * iz2;
         }
-        float4 e0 = f4_splat(0.f), e1 = f4_splat(0.f);
+        float4 e0 = f4_splat(0.f), e1 = f4_splat(0.f), e2 = f4_splat(0.f);
         if (NE >= 1) e0 = *reinterpret_cast<const float4*>(sc + e0off + tg.eoff[k]);
         if (NE >= 2) e1 = *reinterpret_cast<const float4*>(sc + e1off + tg.eoff[k]);
-        epi(plane_off + tg.goff[k], c, q, nvalid, e0, e1);
+        if (NE >= 3) e2 = *reinterpret_cast<const float4*>(sc + e1off + cfg.TY * pitch + tg.eoff[k]);
+        epi(plane_off + tg.goff[k], c, q, nvalid, e0, e1, e2);
     }
 }
 
 // Branch-free variant for tiles that lie completely inside the grid in y, planes without constant z ghosts and
 // non-constant x boundaries: every thread owns exactly G full groups.
-template <int DIM, int NH, int NE, int G, class Epi>
+// In 3-D a thread owns the same cells on every plane of a unit, so the (combined) values of planes z-1 and z are carried
+// in registers from plane to plane (ZMarch) and only plane z+1 is read from shared memory.
+struct ZMarch { float4 m[2], c[2]; bool have; };      // only used with <= 2 groups per thread (register budget)
+
+template <int DIM, int NH, int NE, int G, bool MARCH, class Epi>
 __device__ __forceinline__ void ring_compute_fast(const RingCfg& cfg, const DGrid& g, const ThreadGroups& tg,
                                                   const float* sm, const float* sc, const float* sp, float beta,
-                                                  long long plane_off, Epi& epi)
+                                                  long long plane_off, Epi& epi, ZMarch& zs)
 {
     const int pitch = cfg.pitch;
     const int h1 = (cfg.TY + 2) * pitch;
@@ -360,43 +385,56 @@ __device__ __forceinline__ void ring_compute_fast(const RingCfg& cfg, const DGri
 #pragma unroll
     for (int k = 0; k < G; ++k) {
         const int rc = tg.soff[k];
-        const float4 c = val4(sc, rc);
+        constexpr bool MZ = MARCH && DIM == 3 && G <= 2;
+        const float4 c = (MZ && zs.have) ? zs.c[k & 1] : val4(sc, rc);
         const float4 ym = val4(sc, rc - pitch);
         const float4 yp = val4(sc, rc + pitch);
         float xl = __shfl_up_sync(0xffffffffu, c.w, 1);
         float xr = __shfl_down_sync(0xffffffffu, c.x, 1);
-        if (tg.needl & (1u << k)) { xl = sc[tg.xlo[k]]; if (use1) xl = fmaf(beta, sc[h1 + tg.xlo[k]], xl); }
-        if (tg.needr & (1u << k)) { xr = sc[tg.xro[k]]; if (use1) xr = fmaf(beta, sc[h1 + tg.xro[k]], xr); }
+        if (MARCH) {        // latency-bound single-CTA kernels: every lane loads (broadcast address for most), then selects
+            float el = sc[tg.xlo[k]], er = sc[tg.xro[k]];
+            if (use1) { el = fmaf(beta, sc[h1 + tg.xlo[k]], el); er = fmaf(beta, sc[h1 + tg.xro[k]], er); }
+            xl = (tg.needl & (1u << k)) ? el : xl;
+            xr = (tg.needr & (1u << k)) ? er : xr;
+        } else {
+            if (tg.needl & (1u << k)) { xl = sc[tg.xlo[k]]; if (use1) xl = fmaf(beta, sc[h1 + tg.xlo[k]], xl); }
+            if (tg.needr & (1u << k)) { xr = sc[tg.xro[k]]; if (use1) xr = fmaf(beta, sc[h1 + tg.xro[k]], xr); }
+        }
         float4 q;
         q.x = fmaf(ix2, xl + c.y, fmaf(iy2, ym.x + yp.x, -cc * c.x));
         q.y = fmaf(ix2, c.x + c.z, fmaf(iy2, ym.y + yp.y, -cc * c.y));
         q.z = fmaf(ix2, c.y + c.w, fmaf(iy2, ym.z + yp.z, -cc * c.z));
         q.w = fmaf(ix2, c.z + xr, fmaf(iy2, ym.w + yp.w, -cc * c.w));
         if (DIM == 3) {
-            const float4 zm = val4(sm, rc);
+            const float4 zm = (MZ && zs.have) ? zs.m[k & 1] : val4(sm, rc);
             const float4 zp = val4(sp, rc);
             q.x = fmaf(iz2, zm.x + zp.x, q.x);
             q.y = fmaf(iz2, zm.y + zp.y, q.y);
             q.z = fmaf(iz2, zm.z + zp.z, q.z);
             q.w = fmaf(iz2, zm.w + zp.w, q.w);
+            if (MZ) { zs.m[k & 1] = c; zs.c[k & 1] = zp; }
         }
-        float4 e0 = f4_splat(0.f), e1 = f4_splat(0.f);
+        float4 e0 = f4_splat(0.f), e1 = f4_splat(0.f), e2 = f4_splat(0.f);
         if (NE >= 1) e0 = *reinterpret_cast<const float4*>(sc + e0off + tg.eoff[k]);
         if (NE >= 2) e1 = *reinterpret_cast<const float4*>(sc + e1off + tg.eoff[k]);
-        epi(plane_off + tg.goff[k], c, q, 4, e0, e1);
+        if (NE >= 3) e2 = *reinterpret_cast<const float4*>(sc + e1off + cfg.TY * pitch + tg.eoff[k]);
+        epi(plane_off + tg.goff[k], c, q, 4, e0, e1, e2);
     }
+    zs.have = MARCH && DIM == 3 && G <= 2;
 }
 
-template <bool GENERIC, int DIM, int NH, int NE, class Epi>
+template <bool GENERIC, int DIM, int NH, int NE, bool MARCH, class Epi>
 __device__ __forceinline__ void ring_compute_any(const RingCfg& cfg, const DGrid& g, const DField& pf, const ThreadGroups& tg,
                                                  bool fast, const float* sm, const float* sc, const float* sp, float beta,
-                                                 long long plane_off, int z, Epi& epi)
+                                                 long long plane_off, int z, Epi& epi, ZMarch& zs)
 {
+    if (cfg.dbg & 4) return;
     if (!GENERIC || fast) {
-        if (cfg.groups == 4) { ring_compute_fast<DIM, NH, NE, 4>(cfg, g, tg, sm, sc, sp, beta, plane_off, epi); return; }
-        if (cfg.groups == 2) { ring_compute_fast<DIM, NH, NE, 2>(cfg, g, tg, sm, sc, sp, beta, plane_off, epi); return; }
-        if (cfg.groups == 1) { ring_compute_fast<DIM, NH, NE, 1>(cfg, g, tg, sm, sc, sp, beta, plane_off, epi); return; }
+        if (cfg.groups == 4) { ring_compute_fast<DIM, NH, NE, 4, MARCH>(cfg, g, tg, sm, sc, sp, beta, plane_off, epi, zs); return; }
+        if (cfg.groups == 2) { ring_compute_fast<DIM, NH, NE, 2, MARCH>(cfg, g, tg, sm, sc, sp, beta, plane_off, epi, zs); return; }
+        if (cfg.groups == 1) { ring_compute_fast<DIM, NH, NE, 1, MARCH>(cfg, g, tg, sm, sc, sp, beta, plane_off, epi, zs); return; }
     }
+    zs.have = false;
     if (GENERIC) ring_compute<DIM, NH, NE>(cfg, g, pf, tg, sm, sc, sp, beta, plane_off, z, epi);
 }
 
@@ -414,13 +452,13 @@ __device__ __forceinline__ RingUnit ring_unit(const RingCfg& cfg, const DGrid& g
     return u;
 }
 
-template <bool GENERIC, int DIM, int NH, int NE, class Epi>
+template <bool GENERIC, int DIM, int NH, int NE, bool MARCH = true, class Epi>
 __device__ __forceinline__ void ring_process_unit(Ring& rg, const RingCfg& cfg, const DGrid& g, const DField& pf,
                                                   ThreadGroups& tg,
                                                   const float* const* hsrc, const float* const* esrc, float beta,
                                                   const RingUnit& u, Epi& epi)
 {
-    const bool producer = threadIdx.x >= RING_CONSUMERS;
+    const bool producer = (int)threadIdx.x >= cfg.consumers;
     if (producer) {
         const int nh = (NH == 2 && beta == 0.f) ? 1 : NH;          // first CG iteration: d' = r, old direction not read
         ProdUnit pu;
@@ -443,14 +481,15 @@ __device__ __forceinline__ void ring_process_unit(Ring& rg, const RingCfg& cfg, 
         const int nz = u.z1 - u.z0;
         SlotIt a = rg.pos, bq = a; bq.next(cfg.R);
         SlotIt c2 = bq; c2.next(cfg.R);
+        ZMarch zs; zs.have = false;
         ring_wait_full(rg, a); ring_wait_full(rg, bq);
         for (int zi = 0; zi < nz; ++zi) {
             const int z = u.z0 + zi;
             const bool fast = tile_fast && !(z == 0 && pf.klo[2] == PHI_BC_CONST) && !(z == g.n[2] - 1 && pf.khi[2] == PHI_BC_CONST);
             ring_wait_full(rg, c2);
             epi.set_plane(z, g.n[2]);
-            ring_compute_any<GENERIC, DIM, NH, NE>(cfg, g, pf, tg, fast, ring_ptr(rg, cfg, a), ring_ptr(rg, cfg, bq), ring_ptr(rg, cfg, c2),
-                                          beta, plane_off, z, epi);
+            ring_compute_any<GENERIC, DIM, NH, NE, MARCH>(cfg, g, pf, tg, fast, ring_ptr(rg, cfg, a), ring_ptr(rg, cfg, bq), ring_ptr(rg, cfg, c2),
+                                          beta, plane_off, z, epi, zs);
             ring_release(rg, a);
             a = bq; bq = c2; c2.next(cfg.R);
             plane_off += pf.sz;
@@ -462,7 +501,8 @@ __device__ __forceinline__ void ring_process_unit(Ring& rg, const RingCfg& cfg, 
         ring_wait_full(rg, a);
         const float* sc = ring_ptr(rg, cfg, a);
         epi.set_plane(-1, 0);
-        ring_compute_any<GENERIC, DIM, NH, NE>(cfg, g, pf, tg, tile_fast, sc, sc, sc, beta, plane_off, 0, epi);
+        ZMarch zs; zs.have = false;
+        ring_compute_any<GENERIC, DIM, NH, NE, MARCH>(cfg, g, pf, tg, tile_fast, sc, sc, sc, beta, plane_off, 0, epi, zs);
         ring_release(rg, a);
         rg.pos.next(cfg.R);
     }
@@ -491,7 +531,7 @@ template <bool AXPY>
 struct REpiLaplace {
     float* y; float coeff;
     __device__ __forceinline__ void set_plane(int, int) {}
-    __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid, const float4&, const float4&)
+    __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid, const float4&, const float4&, const float4&)
     {
         float4 o = q;
         if (AXPY) { o.x = c.x + coeff * q.x; o.y = c.y + coeff * q.y; o.z = c.z + coeff * q.z; o.w = c.w + coeff * q.w; }
@@ -503,7 +543,7 @@ struct REpiLaplace {
 struct REpiResidual0 {          // e0 = rhs
     float* r; float mean, offs; float acc0, acc1; PeerHalo ph;
     __device__ __forceinline__ void set_plane(int z, int nz) { ph.set_plane(z, nz); }
-    __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid, const float4& y, const float4&)
+    __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid, const float4& y, const float4&, const float4&)
     {
         float4 rt = make_float4((y.x - mean) - q.x, (y.y - mean) - q.y, (y.z - mean) - q.z, (y.w - mean) - q.w);
         float4 rr = make_float4(rt.x - offs, rt.y - offs, rt.z - offs, rt.w - offs);
@@ -519,7 +559,7 @@ struct REpiResidual0 {          // e0 = rhs
 struct REpiPassA {
     float* dnew; float acc0, acc1; PeerHalo ph;
     __device__ __forceinline__ void set_plane(int z, int nz) { ph.set_plane(z, nz); }
-    __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid, const float4&, const float4&)
+    __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid, const float4&, const float4&, const float4&)
     {
         if (nvalid == 4) {
             *reinterpret_cast<float4*>(dnew + off) = c;
@@ -530,12 +570,30 @@ struct REpiPassA {
     }
 };
 
-struct REpiPassB {              // e0 = x, e1 = r
-    float* x; float* r; float alpha, offs; float acc0, acc1; PeerHalo ph;
+// The solution update is applied every second iteration only: x_{k+1} = x_{k-1} + alpha_{k-1} d_{k-1} + alpha_k d_k needs
+// the previous direction (still intact in the other d buffer) but saves one read+write of x: 30 instead of 32 B/cell/it.
+struct REpiPassBr {             // odd iterations: e0 = r; x is left alone
+    float* r; float alpha, offs; float acc0, acc1; PeerHalo ph;
     __device__ __forceinline__ void set_plane(int z, int nz) { ph.set_plane(z, nz); }
-    __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid, const float4& xe, const float4& re)
+    __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid, const float4& re, const float4&, const float4&)
+    {
+        float4 rv = re;
+        rv.x -= alpha * (q.x + offs); rv.y -= alpha * (q.y + offs); rv.z -= alpha * (q.z + offs); rv.w -= alpha * (q.w + offs);
+        if (nvalid == 4) {
+            *reinterpret_cast<float4*>(r + off) = rv;
+            if (ph.zf) ph.put4(off, rv);
+            acc0 += rv.x * rv.x + rv.y * rv.y + rv.z * rv.z + rv.w * rv.w;
+        } else for (int j = 0; j < nvalid; ++j) { const float t = f4_get(rv, j); r[off + j] = t; if (ph.zf) ph.put1(off + j, t); acc0 += t * t; }
+    }
+};
+
+struct REpiPassB {              // even iterations: e0 = x, e1 = r, e2 = previous direction
+    float* x; float* r; float alpha, aprev, offs; float acc0, acc1; PeerHalo ph;
+    __device__ __forceinline__ void set_plane(int z, int nz) { ph.set_plane(z, nz); }
+    __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid, const float4& xe, const float4& re, const float4& dp)
     {
         float4 xv = xe, rv = re;
+        xv.x += aprev * dp.x; xv.y += aprev * dp.y; xv.z += aprev * dp.z; xv.w += aprev * dp.w;
         xv.x += alpha * c.x; xv.y += alpha * c.y; xv.z += alpha * c.z; xv.w += alpha * c.w;
         rv.x -= alpha * (q.x + offs); rv.y -= alpha * (q.y + offs); rv.z -= alpha * (q.z + offs); rv.w -= alpha * (q.w + offs);
         if (nvalid == 4) {
@@ -562,7 +620,7 @@ k_laplace_ring(DGrid g, DField f, RingCfg cfg, const float* __restrict__ x, floa
     REpiLaplace<AXPY> epi{y, coeff};
     for (int unit = blockIdx.x; unit < cfg.total_units; unit += gridDim.x) {
         const RingUnit u = ring_unit<DIM>(cfg, g, unit);
-        ring_process_unit<GENERIC, DIM, 1, 0>(rg, cfg, g, f, tg, hsrc, esrc, 0.f, u, epi);
+        ring_process_unit<GENERIC, DIM, 1, 0, false>(rg, cfg, g, f, tg, hsrc, esrc, 0.f, u, epi);
     }
 }
 
@@ -629,7 +687,7 @@ __device__ __forceinline__ void ring_unit_cells(const RingCfg& cfg, const DGrid&
                                                 const RingUnit& u, F&& fn)
 {
     // plain element-wise traversal of a unit by the consumer threads (sums, mean removal); no staging
-    if (threadIdx.x >= RING_CONSUMERS) return;
+    if ((int)threadIdx.x >= cfg.consumers) return;
     long long plane_off = (long long)u.b * pf.sb + (long long)u.y0 * pf.sy + (DIM == 3 ? (long long)u.z0 * pf.sz : 0);
     for (int z = u.z0; z < u.z1; ++z, plane_off += pf.sz)
 #pragma unroll
@@ -732,7 +790,7 @@ k_cg_ring(CgRingArgs A)
         const bool divg = !isfinite((float)d0);
         sh.conv[b] = conv; sh.divg[b] = divg; sh.iters[b] = 0;
         sh.cont[b] = (!conv && !divg && a.prm.max_iter > 0) ? 1 : 0;
-        sh.beta[b] = 0.f; sh.alpha[b] = 0.f;
+        sh.beta[b] = 0.f; sh.alpha[b] = 0.f; sh.aprev[b] = 0.f;
     }
     __syncthreads();
     if (threadIdx.x == 0) { int any = 0; for (int b = 0; b < batch; ++b) any |= sh.cont[b]; *sh.any_cont = any; }
@@ -740,8 +798,9 @@ k_cg_ring(CgRingArgs A)
 
     float* dold = a.d0; float* dnew = a.d1;
     float* lo_dnew = cm.lo_d1; float* hi_dnew = cm.hi_d1; float* lo_dold = cm.lo_d0; float* hi_dold = cm.hi_d0;
+    bool x_pending = false;      // all running entries are at the same iteration, so one flag describes them all
     while (*sh.any_cont && comm_ok) {
-        {   // pass A
+        if (!(cfg.dbg & 1)) {   // pass A
             const float* hsrc[2] = {a.r, dold};
             const float* esrc[2] = {nullptr, nullptr};
             sweep(sh.cont, [&](const RingUnit& u, float& acc0, float& acc1) {
@@ -755,19 +814,29 @@ k_cg_ring(CgRingArgs A)
             if (!sh.cont[b]) continue;
             const double S = sh.sum1[b];
             const double dq = sh.sum0[b] + (double)coffs * S * S;
+            sh.aprev[b] = sh.alpha[b];
             sh.alpha[b] = (dq != 0.0) ? (float)(sh.delta[b] / dq) : 0.f;
             sh.offs[b] = coffs * (float)S;
         }
         __syncthreads();
-        {   // pass B
+        if (cfg.dbg & 2) {} else if (!x_pending) {   // pass B, odd iteration: r only, the x update is deferred
             const float* hsrc[2] = {dnew, nullptr};
-            const float* esrc[2] = {a.x, a.r};
+            const float* esrc[3] = {a.r, nullptr, nullptr};
             sweep(sh.cont, [&](const RingUnit& u, float& acc0, float& acc1) {
-                REpiPassB epi{a.x, a.r, sh.alpha[u.b], sh.offs[u.b], 0.f, 0.f, peer_halo(cm.lo_r, cm.hi_r)};
-                ring_process_unit<GENERIC, DIM, 1, 2>(rg, cfg, g, a.pf, tg, hsrc, esrc, 0.f, u, epi);
+                REpiPassBr epi{a.r, sh.alpha[u.b], sh.offs[u.b], 0.f, 0.f, peer_halo(cm.lo_r, cm.hi_r)};
+                ring_process_unit<GENERIC, DIM, 1, 1>(rg, cfg, g, a.pf, tg, hsrc, esrc, 0.f, u, epi);
+                acc0 += epi.acc0;
+            });
+        } else {            // pass B, even iteration: x += alpha_prev d_prev + alpha d
+            const float* hsrc[2] = {dnew, nullptr};
+            const float* esrc[3] = {a.x, a.r, dold};
+            sweep(sh.cont, [&](const RingUnit& u, float& acc0, float& acc1) {
+                REpiPassB epi{a.x, a.r, sh.alpha[u.b], sh.aprev[u.b], sh.offs[u.b], 0.f, 0.f, peer_halo(cm.lo_r, cm.hi_r)};
+                ring_process_unit<GENERIC, DIM, 1, 3>(rg, cfg, g, a.pf, tg, hsrc, esrc, 0.f, u, epi);
                 acc0 += epi.acc0;
             });
         }
+        x_pending = !x_pending;
         barrier_and_reduce(sh.cont);
         for (int b = threadIdx.x; b < batch; b += blockDim.x) {
             if (!sh.cont[b]) continue;
@@ -788,6 +857,21 @@ k_cg_ring(CgRingArgs A)
         float* t = dold; dold = dnew; dnew = t;
         t = lo_dold; lo_dold = lo_dnew; lo_dnew = t;
         t = hi_dold; hi_dold = hi_dnew; hi_dnew = t;
+    }
+
+    // entries that stopped after an odd number of iterations still owe x their last step; odd iterations write d1
+    for (int unit = blockIdx.x; unit < cfg.total_units; unit += gridDim.x) {
+        const RingUnit u = ring_unit<DIM>(cfg, g, unit);
+        if (!(sh.iters[u.b] & 1)) continue;
+        const float al = sh.alpha[u.b];
+        ring_unit_cells<DIM>(cfg, g, a.pf, tg, u, [&](long long off, int nvalid) {
+            if (nvalid == 4) {
+                float4 xv = *reinterpret_cast<const float4*>(a.x + off);
+                const float4 dv = *reinterpret_cast<const float4*>(a.d1 + off);
+                xv.x += al * dv.x; xv.y += al * dv.y; xv.z += al * dv.z; xv.w += al * dv.w;
+                *reinterpret_cast<float4*>(a.x + off) = xv;
+            } else for (int j = 0; j < nvalid; ++j) a.x[off + j] += al * a.d1[off + j];
+        });
     }
 
     if (a.prm.project_mean) {
@@ -822,9 +906,10 @@ static const int kSmemBudget = 227 * 1024;
 
 // lines staged per stage = lines_a * TY + lines_b; returns false when the grid lines are too long for a useful ring
 static bool ring_config(const DGrid& g, int lines_a, int lines_b, int reserve_bytes, int min_stages, int max_stages,
-                        int target_units, RingCfg* out)
+                        int target_units, RingCfg* out, int consumers = RING_CONSUMERS)
 {
     RingCfg c;
+    c.consumers = consumers;
     c.pitch = g.cext[0]; c.nx4 = g.cext[0] / 4;
     const int row_bytes = c.pitch * 4;
     // measured on B200 (512^3): TY=4 beats TY=8 for both laplace (6.12 vs 5.85 TB/s) and CG (5.18 vs 5.10 TB/s): smaller
@@ -833,16 +918,19 @@ static bool ring_config(const DGrid& g, int lines_a, int lines_b, int reserve_by
     if (const char* e = getenv("PHICUDA_RING_TY")) { const int v = atoi(e); if (v >= 1 && v <= ty) ty = v; }     // tuning knob
     for (;; ty /= 2) {
         if (ty < 1) return false;
-        if (ty * c.nx4 > RING_G * RING_CONSUMERS) continue;                    // <= RING_G groups per thread
+        if (ty * c.nx4 > RING_G * consumers) continue;                    // <= RING_G groups per thread
         if (lines_a * ty + lines_b > 128) continue;                            // <= 4 lines per producer lane
         const int stage_bytes = (lines_a * ty + lines_b) * row_bytes;
         const int r = (kSmemBudget - reserve_bytes - 128) / stage_bytes;
+        if (const char* e = getenv("PHICUDA_RING_R")) { const int v = atoi(e); if (v >= min_stages && v < max_stages) max_stages = v; }   // tuning knob
         if (r >= min_stages) { c.TY = ty; c.R = r > max_stages ? max_stages : r; c.stage_floats = stage_bytes / 4; break; }
     }
     while (g.dim == 2 && c.TY > 1 && c.TY / 2 >= g.n[1]) c.TY /= 2;
-    c.groups = (c.TY * c.nx4 + RING_CONSUMERS - 1) / RING_CONSUMERS;
+    c.groups = (c.TY * c.nx4 + consumers - 1) / consumers;
     c.shfl_ok = (c.nx4 % 32 == 0) ? 1 : 0;
     { const char* e = getenv("PHICUDA_RING_HINT"); c.hint = (e && e[0] == '1') ? 1 : 0; }
+    { const char* e = getenv("PHICUDA_RING_MERGE"); c.merge = (e && e[0] == '0') ? 0 : 1; }
+    { const char* e = getenv("PHICUDA_RING_DEBUG"); c.dbg = e ? atoi(e) : 0; }
     if (g.dim == 3) {
         c.nyt = (g.n[1] + c.TY - 1) / c.TY;
         // z chunking: every unit pays a pipeline refill + two halo planes (~ (ZC+2)/ZC), and the persistent grid of
@@ -878,7 +966,7 @@ static bool ring_config(const DGrid& g, int lines_a, int lines_b, int reserve_by
 // every tile and plane of the grid qualifies for the branch-free consumer path
 static bool ring_all_fast(const DGrid& g, const DField& f, const RingCfg& c)
 {
-    if (!c.shfl_ok || c.nx4 * 4 != g.n[0] || c.TY * c.nx4 != c.groups * RING_CONSUMERS || g.n[1] % c.TY != 0) return false;
+    if (!c.shfl_ok || c.nx4 * 4 != g.n[0] || c.TY * c.nx4 != c.groups * c.consumers || g.n[1] % c.TY != 0) return false;
     for (int a = 0; a < g.dim; ++a) if (f.klo[a] == PHI_BC_CONST || f.khi[a] == PHI_BC_CONST) return false;
     return c.groups == 1 || c.groups == 2 || c.groups == 4;
 }
@@ -922,7 +1010,8 @@ int phi_launch_cg_ring(const CgLaunch& l, const CommDev* cm, cudaStream_t s)
     CgRingArgs A;
     const int cgs = (int)((cg_smem_bytes(g.batch) + 127) / 128 * 128);
     const int sms = sm_count();
-    if (!ring_config(g, 3, 4, cgs, g.dim == 3 ? 4 : 2, RING_MAX_STAGES, sms, &A.cfg)) return -100;
+    if (!ring_config(g, 4, 2, cgs, g.dim == 3 ? 4 : 2, RING_MAX_STAGES, sms, &A.cfg)) return -100;
+    const int threads = RING_THREADS;
     A.ring_smem_offset = cgs;
     const size_t smem = (size_t)cgs + 128 + (size_t)A.cfg.R * A.cfg.stage_floats * 4;
     int per_sm = 0;
@@ -931,7 +1020,7 @@ int phi_launch_cg_ring(const CgLaunch& l, const CommDev* cm, cudaStream_t s)
     const void* fn = g.dim == 3 ? (generic ? (const void*)k_cg_ring<3, true> : (const void*)k_cg_ring<3, false>)
                                 : (generic ? (const void*)k_cg_ring<2, true> : (const void*)k_cg_ring<2, false>);
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, RING_THREADS, smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem);
     if (e != cudaSuccess || per_sm < 1) return -100;
     int grid = sms * per_sm;
     if (grid > A.cfg.total_units) grid = A.cfg.total_units;
@@ -948,7 +1037,7 @@ int phi_launch_cg_ring(const CgLaunch& l, const CommDev* cm, cudaStream_t s)
     a.result = l.result; a.prm = l.prm;
     if (cm) A.cm = *cm; else { memset(&A.cm, 0, sizeof(A.cm)); A.cm.n = 1; A.cm.lower = A.cm.upper = -1; }
     void* args[] = {&A};
-    e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(RING_THREADS), args, smem, s);
+    e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, smem, s);
     if (e != cudaSuccess) { phi_set_error("cg ring: cooperative launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;
 }
