@@ -57,7 +57,7 @@ def main():
             ms_cg = timed(solve, 3)
             info = ops.read_results(dom)
             it = float(np.mean(info['iterations']))
-            cg = cells * (32.0 * it + 32.0) / ms_cg / 1e6
+            cg = cells * (30.0 * it + 32.0) / ms_cg / 1e6
             adv = ''
             if ring:
                 v = [0.3 * torch.randn(dom._shape(dom.fext), device='cuda') for _ in range(dom.dim)]
@@ -68,7 +68,7 @@ def main():
                 adv = f" | advect staggered {ms_a:.3f} ms = {20.0 * dom.dim * cells / ms_a / 1e6:.0f} GB/s, centred {ms_c:.3f} ms = {20.0 * cells / ms_c / 1e6:.0f} GB/s"
                 del v, v2
             print(f"n={n} {'2d x64' if dims2 else '3d'} ring={int(ring)}: laplace {ms:.4f} ms = {lap:.0f} GB/s | "
-                  f"CG {it:.0f} it in {ms_cg:.2f} ms = {ms_cg / max(it, 1) * 1e3:.1f} us/it = {cg:.0f} GB/s (32 B/cell/it){adv}", flush=True)
+                  f"CG {it:.0f} it in {ms_cg:.2f} ms = {ms_cg / max(it, 1) * 1e3:.1f} us/it = {cg:.0f} GB/s (30 B/cell/it){adv}", flush=True)
             del x, y, rhs, p, dom
             torch.cuda.empty_cache()
 
