@@ -251,6 +251,35 @@ def test_cg_poisson(vname, rtol):
         np.testing.assert_allclose(got[b], xr, rtol=0, atol=20 * rtol * np.abs(xr).max())
 
 
+@pytest.mark.parametrize('vname', ['periodic3', 'mixed3', 'periodic'])
+def test_cg_truncated_iterates_match_oracle(vname):
+    """The solution after exactly k iterations equals the reference recurrence for odd and even k: the ring kernel applies the
+    x update only every second iteration and settles the last step at the end (Shewchuk CG, _linalg.py:72-87)."""
+    vbc = ALL_V[vname]
+    d = len(vbc)
+    res = (64, 48) if d == 2 else (64, 12, 10)
+    dx = dx_of(d)
+    rng = np.random.default_rng(21)
+    batch = 2
+    dom = ops.Domain(res, dx, batch, vbc=vbc)
+    rhs = rng.standard_normal((batch,) + res).astype(np.float32)
+    rhs[1] *= 3.0
+    A = O.poisson_matrix(res, dx, O.pressure_bc(vbc))
+    rank_def = not O.is_flexible(vbc)
+    for k in (1, 2, 3, 4, 7):
+        prm = ops.cg_params(vbc, rtol=1e-12, atol=0.0, max_iter=k)
+        got = dom.centered_to_numpy(ops.cg_poisson(dom, vbc, dom.centered_from_numpy(rhs), None, prm), squeeze=False)
+        info = ops.read_results(dom)
+        for b in range(batch):
+            y = rhs[b] - rhs[b].mean() if rank_def else rhs[b]
+            ref = O.cg(A, y, np.zeros(res, np.float32), 1e-12, 0.0, k, None)
+            assert info['iterations'][b] == k == ref['iterations'] and info['converged'][b] == 0
+            xr = ref['x'].reshape(res)
+            if rank_def:
+                xr = xr - xr.mean()
+            np.testing.assert_allclose(got[b], xr, rtol=0, atol=2e-5 * max(1.0, np.abs(xr).max()))
+
+
 def test_cg_matrix_offset_matches_reference_formulation():
     """With the rank-1 offset c of _optimize.py:705-714 the iterates follow the reference's (A + c 11^T) system."""
     vbc = BCS3['periodic3']
