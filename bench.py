@@ -251,13 +251,17 @@ def run_e2e(sim, args, torch):
     one()
     torch.cuda.synchronize()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    _, res_dev = sim.dom.workspace()
+    its = []
     t0.record()
     for _ in range(steps):
         one()
+        its.append(res_dev[:1].clone())
     t1.record()
     torch.cuda.synchronize()
     ms = t0.elapsed_time(t1) / steps
     return {"value": 1e3 / ms, "unit": "steps/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": steps,
+            "cg_iterations_per_step": float(torch.cat(its).float().mean().item()),
             "note": "full state (v, s, p) in pinned host arrays in reference (x,y,z) order; upload + transpose + step + transpose + download"}
 
 

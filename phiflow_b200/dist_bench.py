@@ -40,15 +40,18 @@ def run_e2e(sim, slab, args, dev):
     dist.barrier()
     torch.cuda.synchronize()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    its = []
     t0.record()
     for _ in range(steps):
         one()
+        its.append(slab.result_tensor()[:1].clone())
     t1.record()
     torch.cuda.synchronize()
     dist.barrier()
     ms = torch.tensor([t0.elapsed_time(t1) / steps], device=dev, dtype=torch.float64)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     return {"value": 1e3 / float(ms.item()), "unit": "steps/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": steps,
+            "cg_iterations_per_step": float(torch.cat(its).float().mean().item()),
             "note": "per rank: slab state (v, s, p) in pinned host arrays in reference (x,y,z) order; upload + transpose + step + transpose + download"}
 
 
