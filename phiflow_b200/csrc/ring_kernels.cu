@@ -16,6 +16,7 @@
 // thread precomputes the geometry of the <= 4 float4 groups it owns once per kernel, boundary flags once per tile, and
 // the common case runs a branch-free path: 5 LDS.128 + 2 SHFL + ~40 FP32 ops + 1 STG.128 per group.
 #include <cooperative_groups.h>
+#include <type_traits>
 #include "cg_common.cuh"
 #include <cstdlib>
 #include <cstring>
@@ -452,6 +453,37 @@ __device__ __forceinline__ RingUnit ring_unit(const RingCfg& cfg, const DGrid& g
     return u;
 }
 
+// consumers, 3-D: march through the planes of one unit.  G > 0: every plane takes the branch-free path with G groups.
+template <bool GENERIC, int NH, int NE, bool MARCH, int G, class Epi>
+__device__ __forceinline__ void ring_consume_planes(Ring& rg, const RingCfg& cfg, const DGrid& g, const DField& pf, const ThreadGroups& tg,
+                                                    bool tile_fast, float beta, long long plane_off, const RingUnit& u, Epi& epi)
+{
+    const int nz = u.z1 - u.z0;
+    SlotIt a = rg.pos, bq = a; bq.next(cfg.R);
+    SlotIt c2 = bq; c2.next(cfg.R);
+    ZMarch zs; zs.have = false;
+    ring_wait_full(rg, a); ring_wait_full(rg, bq);
+    for (int zi = 0; zi < nz; ++zi) {
+        const int z = u.z0 + zi;
+        ring_wait_full(rg, c2);
+        epi.set_plane(z, g.n[2]);
+        if (G > 0) {
+            if (!(cfg.dbg & 4))
+                ring_compute_fast<3, NH, NE, (G > 0 ? G : 1), MARCH>(cfg, g, tg, ring_ptr(rg, cfg, a), ring_ptr(rg, cfg, bq), ring_ptr(rg, cfg, c2),
+                                                                     beta, plane_off, epi, zs);
+        } else {
+            const bool fast = tile_fast && !(z == 0 && pf.klo[2] == PHI_BC_CONST) && !(z == g.n[2] - 1 && pf.khi[2] == PHI_BC_CONST);
+            ring_compute_any<GENERIC, 3, NH, NE, MARCH>(cfg, g, pf, tg, fast, ring_ptr(rg, cfg, a), ring_ptr(rg, cfg, bq), ring_ptr(rg, cfg, c2),
+                                                        beta, plane_off, z, epi, zs);
+        }
+        ring_release(rg, a);
+        a = bq; bq = c2; c2.next(cfg.R);
+        plane_off += pf.sz;
+    }
+    ring_release(rg, a); ring_release(rg, bq);
+    rg.pos = c2;
+}
+
 template <bool GENERIC, int DIM, int NH, int NE, bool MARCH = true, class Epi>
 __device__ __forceinline__ void ring_process_unit(Ring& rg, const RingCfg& cfg, const DGrid& g, const DField& pf,
                                                   ThreadGroups& tg,
@@ -478,24 +510,11 @@ __device__ __forceinline__ void ring_process_unit(Ring& rg, const RingCfg& cfg, 
     if (GENERIC) groups_tile(tg, cfg, g, pf, u.y0);      // also needed on fast tiles: planes with constant z ghosts take the slow path
     long long plane_off = (long long)u.b * pf.sb + (long long)u.y0 * pf.sy + (DIM == 3 ? (long long)u.z0 * pf.sz : 0);
     if (DIM == 3) {
-        const int nz = u.z1 - u.z0;
-        SlotIt a = rg.pos, bq = a; bq.next(cfg.R);
-        SlotIt c2 = bq; c2.next(cfg.R);
-        ZMarch zs; zs.have = false;
-        ring_wait_full(rg, a); ring_wait_full(rg, bq);
-        for (int zi = 0; zi < nz; ++zi) {
-            const int z = u.z0 + zi;
-            const bool fast = tile_fast && !(z == 0 && pf.klo[2] == PHI_BC_CONST) && !(z == g.n[2] - 1 && pf.khi[2] == PHI_BC_CONST);
-            ring_wait_full(rg, c2);
-            epi.set_plane(z, g.n[2]);
-            ring_compute_any<GENERIC, DIM, NH, NE, MARCH>(cfg, g, pf, tg, fast, ring_ptr(rg, cfg, a), ring_ptr(rg, cfg, bq), ring_ptr(rg, cfg, c2),
-                                          beta, plane_off, z, epi, zs);
-            ring_release(rg, a);
-            a = bq; bq = c2; c2.next(cfg.R);
-            plane_off += pf.sz;
-        }
-        ring_release(rg, a); ring_release(rg, bq);
-        rg.pos = c2;
+        // kernels that contain only the branch-free path pick the group count once per unit, not once per plane
+        if (!GENERIC && cfg.groups == 2) ring_consume_planes<GENERIC, NH, NE, MARCH, 2>(rg, cfg, g, pf, tg, tile_fast, beta, plane_off, u, epi);
+        else if (!GENERIC && cfg.groups == 4) ring_consume_planes<GENERIC, NH, NE, MARCH, 4>(rg, cfg, g, pf, tg, tile_fast, beta, plane_off, u, epi);
+        else if (!GENERIC) ring_consume_planes<GENERIC, NH, NE, MARCH, 1>(rg, cfg, g, pf, tg, tile_fast, beta, plane_off, u, epi);
+        else ring_consume_planes<GENERIC, NH, NE, MARCH, 0>(rg, cfg, g, pf, tg, tile_fast, beta, plane_off, u, epi);
     } else {
         const SlotIt a = rg.pos;
         ring_wait_full(rg, a);
@@ -512,6 +531,13 @@ __device__ __forceinline__ void ring_process_unit(Ring& rg, const RingCfg& cfg, 
 // Multi-GPU: an epilogue that updates a vector whose halo the neighbouring slab needs also stores the first / last owned
 // plane into that neighbour's halo plane through a peer pointer (NVLink).  plo / phi are pre-offset so that the same
 // element offset `off` addresses the right halo plane; zf says whether the current plane is the first (1) / last (2).
+struct NoPeerHalo {            // single-GPU kernels: nothing to store, nothing to test
+    int zf;
+    __device__ __forceinline__ void set_plane(int, int) {}
+    __device__ __forceinline__ void put4(long long, const float4&) const {}
+    __device__ __forceinline__ void put1(long long, float) const {}
+};
+
 struct PeerHalo {
     float* plo; float* phi; int zf;
     __device__ __forceinline__ void set_plane(int z, int nz) { zf = ((z == 0 && plo) ? 1 : 0) | ((z == nz - 1 && phi) ? 2 : 0); }
@@ -540,8 +566,9 @@ struct REpiLaplace {
     }
 };
 
+template <class PH>
 struct REpiResidual0 {          // e0 = rhs
-    float* r; float mean, offs; float acc0, acc1; PeerHalo ph;
+    float* r; float mean, offs; float acc0, acc1; PH ph;
     __device__ __forceinline__ void set_plane(int z, int nz) { ph.set_plane(z, nz); }
     __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid, const float4& y, const float4&, const float4&)
     {
@@ -556,8 +583,9 @@ struct REpiResidual0 {          // e0 = rhs
     }
 };
 
+template <class PH>
 struct REpiPassA {
-    float* dnew; float acc0, acc1; PeerHalo ph;
+    float* dnew; float acc0, acc1; PH ph;
     __device__ __forceinline__ void set_plane(int z, int nz) { ph.set_plane(z, nz); }
     __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid, const float4&, const float4&, const float4&)
     {
@@ -572,8 +600,9 @@ struct REpiPassA {
 
 // The solution update is applied every second iteration only: x_{k+1} = x_{k-1} + alpha_{k-1} d_{k-1} + alpha_k d_k needs
 // the previous direction (still intact in the other d buffer) but saves one read+write of x: 30 instead of 32 B/cell/it.
+template <class PH>
 struct REpiPassBr {             // odd iterations: e0 = r; x is left alone
-    float* r; float alpha, offs; float acc0, acc1; PeerHalo ph;
+    float* r; float alpha, offs; float acc0, acc1; PH ph;
     __device__ __forceinline__ void set_plane(int z, int nz) { ph.set_plane(z, nz); }
     __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid, const float4& re, const float4&, const float4&)
     {
@@ -587,8 +616,9 @@ struct REpiPassBr {             // odd iterations: e0 = r; x is left alone
     }
 };
 
+template <class PH>
 struct REpiPassB {              // even iterations: e0 = x, e1 = r, e2 = previous direction
-    float* x; float* r; float alpha, aprev, offs; float acc0, acc1; PeerHalo ph;
+    float* x; float* r; float alpha, aprev, offs; float acc0, acc1; PH ph;
     __device__ __forceinline__ void set_plane(int z, int nz) { ph.set_plane(z, nz); }
     __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid, const float4& xe, const float4& re, const float4& dp)
     {
@@ -698,7 +728,7 @@ __device__ __forceinline__ void ring_unit_cells(const RingCfg& cfg, const DGrid&
         }
 }
 
-template <int DIM, bool GENERIC>
+template <int DIM, bool GENERIC, bool DIST>
 __global__ void __launch_bounds__(RING_THREADS, 1)
 k_cg_ring(CgRingArgs A)
 {
@@ -746,10 +776,13 @@ k_cg_ring(CgRingArgs A)
         }
     };
     const long long nzsz = (long long)g.n[2] * a.pf.sz;
+    using PH = typename std::conditional<DIST, PeerHalo, NoPeerHalo>::type;
     auto peer_halo = [&](float* lo_arr, float* hi_arr) {
-        PeerHalo ph;
-        ph.plo = (cm.n > 1 && cm.lower >= 0) ? lo_arr + nzsz : nullptr;
-        ph.phi = (cm.n > 1 && cm.upper >= 0) ? hi_arr - nzsz : nullptr;
+        PH ph;
+        if constexpr (DIST) {
+            ph.plo = cm.lower >= 0 ? lo_arr + nzsz : nullptr;
+            ph.phi = cm.upper >= 0 ? hi_arr - nzsz : nullptr;
+        }
         ph.zf = 0;
         return ph;
     };
@@ -775,7 +808,7 @@ k_cg_ring(CgRingArgs A)
         const float* hsrc[2] = {a.x, nullptr};
         const float* esrc[2] = {a.rhs, nullptr};
         sweep(nullptr, [&](const RingUnit& u, float& acc0, float& acc1) {
-            REpiResidual0 epi{a.r, sh.mean[u.b], sh.offs[u.b], 0.f, 0.f, peer_halo(cm.lo_r, cm.hi_r)};
+            REpiResidual0<PH> epi{a.r, sh.mean[u.b], sh.offs[u.b], 0.f, 0.f, peer_halo(cm.lo_r, cm.hi_r)};
             ring_process_unit<GENERIC, DIM, 1, 1>(rg, cfg, g, a.pf, tg, hsrc, esrc, 0.f, u, epi);
             acc0 += epi.acc0; acc1 += epi.acc1;
         });
@@ -804,7 +837,7 @@ k_cg_ring(CgRingArgs A)
             const float* hsrc[2] = {a.r, dold};
             const float* esrc[2] = {nullptr, nullptr};
             sweep(sh.cont, [&](const RingUnit& u, float& acc0, float& acc1) {
-                REpiPassA epi{dnew, 0.f, 0.f, peer_halo(lo_dnew, hi_dnew)};
+                REpiPassA<PH> epi{dnew, 0.f, 0.f, peer_halo(lo_dnew, hi_dnew)};
                 ring_process_unit<GENERIC, DIM, 2, 0>(rg, cfg, g, a.pf, tg, hsrc, esrc, sh.beta[u.b], u, epi);
                 acc0 += epi.acc0; acc1 += epi.acc1;
             });
@@ -823,7 +856,7 @@ k_cg_ring(CgRingArgs A)
             const float* hsrc[2] = {dnew, nullptr};
             const float* esrc[3] = {a.r, nullptr, nullptr};
             sweep(sh.cont, [&](const RingUnit& u, float& acc0, float& acc1) {
-                REpiPassBr epi{a.r, sh.alpha[u.b], sh.offs[u.b], 0.f, 0.f, peer_halo(cm.lo_r, cm.hi_r)};
+                REpiPassBr<PH> epi{a.r, sh.alpha[u.b], sh.offs[u.b], 0.f, 0.f, peer_halo(cm.lo_r, cm.hi_r)};
                 ring_process_unit<GENERIC, DIM, 1, 1>(rg, cfg, g, a.pf, tg, hsrc, esrc, 0.f, u, epi);
                 acc0 += epi.acc0;
             });
@@ -831,7 +864,7 @@ k_cg_ring(CgRingArgs A)
             const float* hsrc[2] = {dnew, nullptr};
             const float* esrc[3] = {a.x, a.r, dold};
             sweep(sh.cont, [&](const RingUnit& u, float& acc0, float& acc1) {
-                REpiPassB epi{a.x, a.r, sh.alpha[u.b], sh.aprev[u.b], sh.offs[u.b], 0.f, 0.f, peer_halo(cm.lo_r, cm.hi_r)};
+                REpiPassB<PH> epi{a.x, a.r, sh.alpha[u.b], sh.aprev[u.b], sh.offs[u.b], 0.f, 0.f, peer_halo(cm.lo_r, cm.hi_r)};
                 ring_process_unit<GENERIC, DIM, 1, 3>(rg, cfg, g, a.pf, tg, hsrc, esrc, 0.f, u, epi);
                 acc0 += epi.acc0;
             });
@@ -1017,8 +1050,11 @@ int phi_launch_cg_ring(const CgLaunch& l, const CommDev* cm, cudaStream_t s)
     int per_sm = 0;
     cudaError_t e;
     const bool generic = !ring_all_fast(g, l.pf, A.cfg);
-    const void* fn = g.dim == 3 ? (generic ? (const void*)k_cg_ring<3, true> : (const void*)k_cg_ring<3, false>)
-                                : (generic ? (const void*)k_cg_ring<2, true> : (const void*)k_cg_ring<2, false>);
+    const bool dist = cm && cm->n > 1;
+#define CG_RING_FN(D, GEN) (dist ? (const void*)k_cg_ring<D, GEN, true> : (const void*)k_cg_ring<D, GEN, false>)
+    const void* fn = g.dim == 3 ? (generic ? CG_RING_FN(3, true) : CG_RING_FN(3, false))
+                                : (generic ? CG_RING_FN(2, true) : CG_RING_FN(2, false));
+#undef CG_RING_FN
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem);
     if (e != cudaSuccess || per_sm < 1) return -100;
