@@ -5,7 +5,8 @@
 Mirrored (same names, argument meaning and error behaviour; reference file:line in each docstring):
     Box, Sphere, CenteredGrid, StaggeredGrid, extrapolation (ZERO, ONE, PERIODIC, ZERO_GRADIENT, BOUNDARY, combine_sides),
     Solve, SolveTape, NotConverged, Diverged, field.{divergence, laplace, spatial_gradient}, resample,
-    advect.{semi_lagrangian, mac_cormack, advect}, diffuse.explicit, fluid.{make_incompressible, incompressible_step}.
+    advect.{semi_lagrangian, mac_cormack, advect}, diffuse.explicit, fluid.{make_incompressible, incompressible_step},
+    write / read (field.write / field.read: the reference's .npz field files, see field_io.py).
 Fields hold device tensors in the library layout; `.numpy()` returns the reference's (x, y[, z]) arrays.
 Anything outside the fast path raises NotImplementedError (where the reference-side façade would fall through to stock
 PhiFlow).  No CPU fallback.
@@ -17,10 +18,11 @@ import numpy as np
 import torch
 
 from . import _ops as ops
+from . import field_io
 
 __all__ = ['Box', 'Sphere', 'CenteredGrid', 'StaggeredGrid', 'extrapolation', 'ZERO', 'ONE', 'PERIODIC', 'ZERO_GRADIENT',
            'BOUNDARY', 'combine_sides', 'Solve', 'SolveTape', 'NotConverged', 'Diverged', 'ConvergenceException', 'field',
-           'resample', 'advect', 'diffuse', 'fluid', 'math']
+           'resample', 'advect', 'diffuse', 'fluid', 'math', 'write', 'read']
 
 AXES = 'xyz'
 
@@ -224,13 +226,21 @@ math = SimpleNamespace(Solve=Solve, SolveTape=SolveTape, NotConverged=NotConverg
 # fields  (phi/field/_field.py, _grid.py)
 # ----------------------------------------------------------------------------------------------------------------------
 _DOMAINS = {}
+_DEVICE = 'cuda'
+
+
+def set_device(device):
+    """Device that newly created fields live on.  'cpu' fields are data containers only (construction, `.numpy()`, file IO);
+    every kernel still requires a CUDA device - there is no CPU fallback."""
+    global _DEVICE
+    _DEVICE = str(device)
 
 
 def _domain(res, dx, batch, vspec):
     upper = tuple(ops.stored_faces(vspec, a)[1] for a in range(len(res))) if vspec is not None else (False,) * len(res)
-    key = (tuple(res), tuple(dx), batch, upper)
+    key = (tuple(res), tuple(dx), batch, upper, _DEVICE)
     if key not in _DOMAINS:
-        _DOMAINS[key] = ops.Domain(res, dx, batch, vbc=vspec)
+        _DOMAINS[key] = ops.Domain(res, dx, batch, vbc=vspec, device=_DEVICE)
     return _DOMAINS[key]
 
 
@@ -473,8 +483,52 @@ def resample(value, to, soft=False, **_):
     raise NotImplementedError("resample: only Sphere->CenteredGrid and (scalar*vector)->StaggeredGrid are on the fast path")
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# file IO  (phi/field/_field_io.py)
+# ----------------------------------------------------------------------------------------------------------------------
+def write(fld, file: str):
+    """field.write(field, file) (phi/field/_field_io.py:13-69): one compressed .npz per field with the reference's keys;
+    a staggered grid is stored as its uniform `staggered_tensor()` ((n+1) points per axis, trailing `vector` dim)."""
+    _require(isinstance(fld, (CenteredGrid, StaggeredGrid)) and isinstance(file, str), "writing anything but one grid to one file")
+    d = len(fld.axes)
+    ext = field_io.extrapolation_to_dict(fld.boundary.default, fld.boundary.sides, fld.axes)
+    lead_names = ('batch',) if fld.batch > 1 else ()
+    lead_types = ('batch',) if fld.batch > 1 else ()
+    lower, upper = [fld.lower[i] for i in range(d)], [fld.upper[i] for i in range(d)]
+    if isinstance(fld, CenteredGrid):
+        field_io.write_single_field(file, 'CenteredGrid', fld.numpy(), lead_names + fld.axes, lead_types + ('spatial',) * d,
+                                    (None,) * (len(lead_names) + d), lower, upper, fld.axes, ext)
+    else:
+        data = field_io.staggered_tensor(fld.numpy(), lambda ax: (fld.boundary.side(fld.axes[ax], False), fld.boundary.side(fld.axes[ax], True)), d)
+        field_io.write_single_field(file, 'StaggeredGrid', data, lead_names + fld.axes + ('vector',), lead_types + ('spatial',) * d + ('channel',),
+                                    (None,) * (len(lead_names) + d) + (fld.axes,), lower, upper, fld.axes, ext)
+
+
+def read(file: str):
+    """field.read(file) (phi/field/_field_io.py:72-127): restores a CenteredGrid / StaggeredGrid written by `write` or by stock
+    PhiFlow (scalar centred grids and staggered grids whose vector components match the spatial dims)."""
+    st = field_io.read_single_field(file)
+    names, types = st['dim_names'], st['dim_types']
+    axes = tuple(n for n, t in zip(names, types) if t == 'spatial')
+    lead = tuple(n for n, t in zip(names, types) if t == 'batch')
+    _require(len(lead) <= 1 and names[:len(lead)] == lead and names[len(lead):len(lead) + len(axes)] == axes, "batch dims after spatial dims")
+    default, sides = field_io.extrapolation_from_dict(st['extrapolation'])
+    boundary = Extrapolation(default, sides)
+    data = np.asarray(st['data'], np.float32)
+    batch = data.shape[0] if lead else 1
+    bounds = Box(**{a: (st['lower'][a], st['upper'][a]) for a in axes})
+    if st['field_type'] == 'CenteredGrid':
+        _require(data.ndim == len(lead) + len(axes), "centred grids with channel dims")
+        res = dict(zip(axes, data.shape[len(lead):]))
+        return CenteredGrid(data, boundary, bounds, batch, **res)
+    _require(names[-1] == 'vector' and data.shape[-1] == len(axes), "staggered tensors whose components are not the spatial dims")
+    comps = field_io.unstack_staggered_tensor(data, lambda ax: (boundary.side(axes[ax], False), boundary.side(axes[ax], True)), len(axes))
+    res = {a: n - 1 for a, n in zip(axes, data.shape[len(lead):len(lead) + len(axes)])}
+    return StaggeredGrid(comps, boundary, bounds, batch, **res)
+
+
 field = SimpleNamespace(divergence=divergence, laplace=laplace, spatial_gradient=spatial_gradient, resample=resample,
-                        CenteredGrid=CenteredGrid, StaggeredGrid=StaggeredGrid)
+                        CenteredGrid=CenteredGrid, StaggeredGrid=StaggeredGrid, write=write, read=read)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
