@@ -534,6 +534,55 @@ def cg(A, y: np.ndarray, x0: np.ndarray, rtol: float, atol: float, max_iter: int
                 residual_sq=float(abs(delta)), tol_sq=float(tol_sq))
 
 
+def cg_adaptive(A, y: np.ndarray, x0: np.ndarray, rtol: float, atol: float, max_iter: int, matrix_offset=None):
+    """CG-adaptive (Hestenes-Stiefel variant), PhiML/phiml/backend/_linalg.py:93-128.  Differences to cg(): the step is
+    (dx.r)/(dx.dy), the new direction is r - ((r.dy)/(dx.dy)) dx with dy = A dx kept from the previous iteration, and the
+    tolerance is relative to |y|^2 (:109), not to the initial residual.  One batch entry; dict as cg() + function_evaluations."""
+    y = y.astype(F32).ravel()
+    x = x0.astype(F32).ravel().copy()
+
+    def linear(vec):
+        res = A.dot(vec).astype(F32)
+        if matrix_offset is not None:
+            res = res + np.sum(vec, dtype=F32) * F32(matrix_offset)
+        return res
+
+    def div_no_nan(a, b):
+        return F32(0) if b == 0 else F32(a / b)
+
+    dx = residual = y - linear(x)
+    dy = linear(dx)
+    iterations, function_evaluations = 0, 1
+    rsq = np.sum(residual ** 2, dtype=F32)
+    tol_sq = max(F32(rtol) ** 2 * np.sum(y ** 2, dtype=F32), F32(atol) ** 2)
+    rsq0 = abs(rsq)
+
+    def check(it, r2, first):
+        r2 = abs(r2)
+        converged = bool(r2 <= tol_sq)
+        if first:
+            diverged = not np.isfinite(r2)
+        else:
+            with np.errstate(divide='ignore', invalid='ignore'):
+                diverged = bool((r2 / rsq0 > 1e5) and it >= 8) or not np.isfinite(r2)
+        return (not converged) and (not diverged) and it < max_iter, converged, diverged
+
+    cont, converged, diverged = check(0, rsq, True)
+    while cont:
+        iterations += 1
+        dx_dy = np.sum(dx * dy, dtype=F32)
+        step = div_no_nan(np.sum(dx * residual, dtype=F32), dx_dy)
+        x = x + step * dx
+        residual = residual - step * dy
+        rsq = np.sum(residual ** 2, dtype=F32)
+        dx = residual - div_no_nan(np.sum(residual * dy, dtype=F32), dx_dy) * dx
+        dy = linear(dx)
+        function_evaluations += 1
+        cont, converged, diverged = check(iterations, rsq, False)
+    return dict(x=x, residual=residual, iterations=iterations, function_evaluations=function_evaluations, converged=converged,
+                diverged=diverged, residual_sq=float(abs(rsq)), tol_sq=float(tol_sq))
+
+
 def make_incompressible(v: List[np.ndarray], vbc, res, dx, rtol=1e-5, atol=1e-5, max_iter=1000, x0=None,
                         use_matrix_offset=True, rng=None, matrix=None):
     """fluid.make_incompressible, no obstacles, order 2, StaggeredGrid: phi/physics/fluid.py:94-162.

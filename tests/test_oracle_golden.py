@@ -112,6 +112,29 @@ def test_cg_matches_phiml_solve_linear(name, tag, rtol):
     np.testing.assert_allclose(info['x'].reshape(res), x_ref, rtol=0, atol=20 * rtol * scale)
 
 
+GOLD_ACG = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'phiml_cg_adaptive.npz'))
+
+
+@pytest.mark.parametrize('name', ['open', 'mixed', 'mixed3'])
+@pytest.mark.parametrize('tag,rtol', [('r3', 1e-3), ('r5', 1e-5)])
+def test_cg_adaptive_matches_phiml_solve_linear(name, tag, rtol):
+    """Solve('CG-adaptive') of the vendored PhiML (_linalg.py:93-128) vs oracle.cg_adaptive on the same pressure systems."""
+    vbc = spec_from_arr(GOLD_ACG[f'{name}/bc'])
+    dx = GOLD_ACG[f'{name}/dx']
+    rhs = GOLD_ACG[f'{name}/rhs']
+    res = rhs.shape
+    A = O.poisson_matrix(res, dx, O.pressure_bc(vbc))
+    assert O.is_flexible(vbc)
+    info = O.cg_adaptive(A, rhs, np.zeros(res, np.float32), rtol, 1e-5, 1000, None)
+    it_ref = int(GOLD_ACG[f'{name}/{tag}/iterations'])
+    assert info['converged'] and not info['diverged']
+    assert abs(info['iterations'] - it_ref) <= max(2, it_ref // 10), (info['iterations'], it_ref)
+    assert info['function_evaluations'] == info['iterations'] + 1
+    assert int(GOLD_ACG[f'{name}/{tag}/function_evaluations']) == it_ref + 1
+    x_ref = GOLD_ACG[f'{name}/{tag}/x']
+    np.testing.assert_allclose(info['x'].reshape(res), x_ref, rtol=0, atol=20 * rtol * np.abs(x_ref).max())
+
+
 # ----------------------------------------------------------------------------------------------------
 # known-answer tests of the reference suite
 # ----------------------------------------------------------------------------------------------------
