@@ -211,6 +211,81 @@ def gradient_faces(p: np.ndarray, dx: Sequence[float], pbc, vbc) -> List[np.ndar
 
 
 # --------------------------------------------------------------------------------------------------
+# Appendix A of SURVEY.md: the CenteredGrid-velocity ("collocated", wide stencil) variant of the projection
+# --------------------------------------------------------------------------------------------------
+
+def gradient_centered(p: np.ndarray, dx: Sequence[float], pbc) -> List[np.ndarray]:
+    """field.spatial_gradient(p, at='center') order 2 (phi/field/_field_math.py:230-233) = math.spatial_gradient
+    'central' (PhiML/phiml/math/_nd.py:810-812): (p[i+1] - p[i-1]) / (2 dx) with ghost p from the pressure boundary."""
+    out = []
+    for c in range(p.ndim):
+        q = pad_axis(p, c, 1, 1, pbc[c])
+        n = p.shape[c]
+        out.append((np.take(q, np.arange(2, n + 2), axis=c) - np.take(q, np.arange(0, n), axis=c)) / (F32(dx[c]) * F32(2)))
+    return out
+
+
+def divergence_centered(v: List[np.ndarray], dx: Sequence[float], vbc_comp) -> np.ndarray:
+    """field.divergence of a CenteredGrid, order 2 (phi/field/_field_math.py:627-632): sum_d (v_d[i+1] - v_d[i-1]) / (2 dx_d)
+    with ghost values from the velocity boundary of component d."""
+    result = None
+    for c, comp in enumerate(v):
+        q = pad_axis(comp, c, 1, 1, vbc_comp[c][c])
+        n = comp.shape[c]
+        term = (np.take(q, np.arange(2, n + 2), axis=c) - np.take(q, np.arange(0, n), axis=c)) / (F32(dx[c]) * F32(2))
+        result = term if result is None else result + term
+    return result
+
+
+def remove_constant_offset(bc):
+    """extrapolation.remove_constant_offset: constants become 0, the rest is kept (fluid.py:200)."""
+    return tuple(tuple(s if isinstance(s, str) else 0.0 for s in ax) for ax in bc)
+
+
+def wide_laplace(p: np.ndarray, dx: Sequence[float], pbc, vbc) -> np.ndarray:
+    """fluid.masked_laplace(wide_stencil=True) without obstacles (phi/physics/fluid.py:197-202): centred divergence of the
+    centred gradient; the gradient's ghosts follow the velocity boundary with constants removed."""
+    d = p.ndim
+    vbc0 = remove_constant_offset(vbc)
+    return divergence_centered(gradient_centered(p, dx, pbc), dx, [vbc0] * d)
+
+
+def wide_poisson_matrix(res: Sequence[int], dx: Sequence[float], vbc) -> sp.csr_matrix:
+    """Matrix of wide_laplace (what jit_compile_linear traces for CenteredGrid velocities): interior rows
+    [1 0 -2 0 1] / (4 dx^2) per axis.  Built column by column from unit vectors (small grids only); C order of (x, y, z)."""
+    n = int(np.prod(res))
+    pbc = pressure_bc(vbc)
+    cols = []
+    for j in range(n):
+        e = np.zeros(n, F32)
+        e[j] = 1
+        cols.append(wide_laplace(e.reshape(res), dx, pbc, vbc).ravel())
+    return sp.csr_matrix(np.stack(cols, axis=1).astype(F32))
+
+
+def make_incompressible_centered(v: List[np.ndarray], vbc, res, dx, rtol=1e-5, atol=1e-5, max_iter=1000, rng=None, method='CG-adaptive'):
+    """fluid.make_incompressible for a CenteredGrid velocity (phi/physics/fluid.py:138-161 with wide_stencil=True, :154-155):
+    centred divergence -> (balance) -> solve on the wide operator (+ the rank-1 offset of _optimize.py:705-714 when the system
+    is rank deficient) -> v -= centred gradient of p.
+    The default Solve() has method 'auto', which the vendored PhiML maps to CG-adaptive (backend/_backend.py:1446-1447).
+    That matters here: the boundary rows of the wide operator are not symmetric (the ghosts of the gradient follow the
+    pressure boundary, those of the divergence the velocity boundary), and plain CG does not reach rtol 1e-5 within 1000
+    iterations on the reference test's systems, CG-adaptive needs 28-43 (measured with this oracle)."""
+    d = len(res)
+    div = divergence_centered(v, dx, component_bcs(vbc, d))
+    pbc = pressure_bc(vbc)
+    A = wide_poisson_matrix(res, dx, vbc)
+    offset = None
+    if not is_flexible(vbc):
+        div = div - np.mean(div, dtype=F32)
+        offset = estimate_matrix_offset(A, div.size, rng if rng is not None else np.random.default_rng(0))
+    info = (cg_adaptive if method == 'CG-adaptive' else cg)(A, div, np.zeros(res, F32), rtol, atol, max_iter, offset)
+    p = info['x'].reshape(res)
+    grad = gradient_centered(p, dx, pbc)
+    return [v[c] - grad[c] for c in range(d)], p, info
+
+
+# --------------------------------------------------------------------------------------------------
 # A11  grid_sample (the NumPy backend has no native grid_sample -> python fallback is the oracle)
 # --------------------------------------------------------------------------------------------------
 

@@ -135,6 +135,53 @@ def test_cg_adaptive_matches_phiml_solve_linear(name, tag, rtol):
     np.testing.assert_allclose(info['x'].reshape(res), x_ref, rtol=0, atol=20 * rtol * np.abs(x_ref).max())
 
 
+GOLD_COL = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'phiml_collocated.npz'))
+
+
+@pytest.mark.parametrize('name', ['zero', 'open', 'periodic', 'mixed', 'one', 'mixed3'])
+def test_collocated_gradient_divergence_matrix_match_phiml(name):
+    """CenteredGrid-velocity variant (fluid.py:154-155,197-202): central gradient, centred divergence
+    and the traced wide-stencil operator of the vendored PhiML vs the oracle."""
+    vbc = spec_from_arr(GOLD_COL[f'{name}/bc'])
+    dx = GOLD_COL[f'{name}/dx']
+    p = GOLD_COL[f'{name}/p']
+    d = p.ndim
+    pbc = O.pressure_bc(vbc)
+    for c, g in enumerate(O.gradient_centered(p, dx, pbc)):
+        np.testing.assert_allclose(g, GOLD_COL[f'{name}/grad{c}'], rtol=1e-6, atol=1e-6)
+    comps = [GOLD_COL[f'{name}/v{c}'] for c in range(d)]
+    np.testing.assert_allclose(O.divergence_centered(comps, dx, O.component_bcs(vbc, d)), GOLD_COL[f'{name}/div'], rtol=1e-6, atol=2e-6)
+    np.testing.assert_allclose(O.wide_laplace(p, dx, pbc, vbc), GOLD_COL[f'{name}/lap'], rtol=1e-5, atol=1e-5)
+    A = O.wide_poisson_matrix(p.shape, dx, vbc)
+    np.testing.assert_allclose(A.toarray(), GOLD_COL[f'{name}/matrix'], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(A.dot(p.ravel()).reshape(p.shape), GOLD_COL[f'{name}/lap'], rtol=1e-5, atol=1e-5)
+
+
+def test_collocated_interior_row_is_the_wide_stencil():
+    """Appendix A: [1 0 -2 0 1] / (4 dx^2) per axis in the interior."""
+    A = O.wide_poisson_matrix((9,), (0.5,), ((0.0, 0.0),)).toarray()
+    np.testing.assert_allclose(A[4, 2:7], np.array([1, 0, -2, 0, 1]) / (4 * 0.25), atol=1e-6)
+
+
+@pytest.mark.parametrize('vbc', [((0.0, 0.0), (0.0, 0.0)), (('zg', 'zg'), ('zg', 'zg'))])
+def test_collocated_projection_removes_centred_divergence(vbc):
+    """tests/commit/physics/test_fluid.py:17-28,34-36 (CenteredGrid with ZERO and BOUNDARY): two rounds of buoyancy from a
+    sphere of smoke + make_incompressible on a 16 x 20 grid over [0,100]^2; the centred divergence ends below 5e-5."""
+    res, dx = (16, 20), (100 / 16, 100 / 20)
+    pts = O.points_of((0.0, 0.0), (100.0, 100.0), res)
+    smoke = (np.sum((pts - np.array([40.0, 10.0], np.float32)) ** 2, -1) <= 25.0).astype(np.float32)
+    v = [np.zeros(res, np.float32), np.zeros(res, np.float32)]
+    for _ in range(2):
+        v = [v[0], v[1] + smoke * np.float32(0.1)]
+        v, p, info = O.make_incompressible_centered(v, vbc, res, dx)          # 'auto' = CG-adaptive in the vendored PhiML
+        assert not info['diverged'] and (info['converged'] or not O.is_flexible(vbc))
+    div = O.divergence_centered(v, dx, O.component_bcs(vbc, 2))
+    assert np.abs(div).max() < 5e-5, np.abs(div).max()                       # the reference test's own tolerance
+    # plain CG is the wrong solver for this operator: its boundary rows make it non-symmetric (walls and open sides alike)
+    A = O.wide_poisson_matrix(res, dx, vbc).toarray()
+    assert np.abs(A - A.T).max() > 1e-3
+
+
 # ----------------------------------------------------------------------------------------------------
 # known-answer tests of the reference suite
 # ----------------------------------------------------------------------------------------------------
