@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PHICUDA_ABI_VERSION 1
+#define PHICUDA_ABI_VERSION 2
 
 /* boundary kinds per side  (PhiML/phiml/math/extrapolation.py:247 ConstantExtrapolation incl. ZERO/ONE,
  * :544 _ZeroGradient == BOUNDARY, :648 _PeriodicExtrapolation; per-side mixes: combine_sides :1209) */
@@ -77,7 +77,13 @@ typedef struct PhiCgParams {
     int32_t project_mean;    /* 1: remove mean(x) at the end (the rank-1 matrix_offset of _optimize.py:705-714 selects
                                 the zero-mean solution of the singular system) */
     float   matrix_offset;   /* c of (A + c 1 1^T); 0 = plain CG on the range space */
+    int32_t method;          /* PHI_SOLVER_CG: Shewchuk CG (_linalg.py:52-90);  PHI_SOLVER_CG_ADAPTIVE: the Hestenes-Stiefel
+                                variant behind Solve('CG-adaptive') and, in PhiML 1.7, Solve('auto') (_linalg.py:93-128,
+                                _backend.py:1446): step (d.r)/(d.Ad), direction r - ((r.Ad)/(d.Ad)) d, tolerance relative
+                                to |y|^2.  Requires matrix_offset == 0. */
 } PhiCgParams;
+#define PHI_SOLVER_CG 0
+#define PHI_SOLVER_CG_ADAPTIVE 1
 
 /* Per batch entry, mirrors SolveResult (PhiML/phiml/backend/_backend.py:24-32). */
 typedef struct PhiCgResult {

@@ -30,7 +30,7 @@ class PhiVBC(C.Structure):
 
 class PhiCgParams(C.Structure):
     _fields_ = [('rtol', C.c_float), ('atol', C.c_float), ('max_iter', C.c_int32), ('balance_rhs', C.c_int32),
-                ('project_mean', C.c_int32), ('matrix_offset', C.c_float)]
+                ('project_mean', C.c_int32), ('matrix_offset', C.c_float), ('method', C.c_int32)]
 
 
 class PhiCgResult(C.Structure):

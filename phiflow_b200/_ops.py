@@ -270,7 +270,7 @@ def _is_flexible(vspec) -> bool:
     return any(side == ZG for ax in spec for side in ax)
 
 
-def cg_params(vbc, rtol=1e-5, atol=1e-5, max_iter=1000, matrix_offset=0.0, balance=None) -> PhiCgParams:
+def cg_params(vbc, rtol=1e-5, atol=1e-5, max_iter=1000, matrix_offset=0.0, balance=None, method='CG') -> PhiCgParams:
     """Solver parameters with the defaults of fluid.make_incompressible (phi/physics/fluid.py:145-148):
     non-flexible velocity boundaries (closed / periodic) -> balanced right-hand side and rank deficiency 1."""
     rank_def = not _is_flexible(vbc)
@@ -279,6 +279,7 @@ def cg_params(vbc, rtol=1e-5, atol=1e-5, max_iter=1000, matrix_offset=0.0, balan
     prm.balance_rhs = int(rank_def if balance is None else balance)
     prm.project_mean = int(rank_def)
     prm.matrix_offset = float(matrix_offset) if rank_def else 0.0
+    prm.method = {'CG': 0, 'CG-adaptive': 1}[method]
     return prm
 
 

@@ -314,10 +314,14 @@ int phi_launch_cg(const CgLaunch& l, cudaStream_t s)
     if (g.batch > CG_MAX_BATCH) { phi_set_error("cg: batch %d exceeds %d (split the batch)", g.batch, CG_MAX_BATCH); return PHI_ERR_UNSUPPORTED; }
     if (l.workspace_bytes < phi_cg_workspace_bytes(g)) { phi_set_error("cg: workspace %zu < %zu bytes", l.workspace_bytes, phi_cg_workspace_bytes(g)); return PHI_ERR_WORKSPACE; }
     const bool mask = l.acc != nullptr;              // obstacles: register-marching kernel (the TMA ring has no mask variant yet)
+    const bool adaptive = l.prm.method == PHI_SOLVER_CG_ADAPTIVE;
+    if (l.prm.method != PHI_SOLVER_CG && !adaptive) { phi_set_error("cg: unknown solver method %d", l.prm.method); return PHI_ERR_INVALID; }
+    if (adaptive && l.prm.matrix_offset != 0.f) { phi_set_error("cg: CG-adaptive does not take a matrix_offset"); return PHI_ERR_UNSUPPORTED; }
     if (phi_ring_enabled() && !mask) {
         const int e = phi_launch_cg_ring(l, nullptr, s);
         if (e != -100) return e;
     }
+    if (adaptive) { phi_set_error("cg: CG-adaptive runs on the TMA ring kernel only (no obstacles, grid lines must fit the ring)"); return PHI_ERR_UNSUPPORTED; }
     if (mask && l.prm.matrix_offset != 0.f) { phi_set_error("cg: matrix_offset is not supported together with obstacles"); return PHI_ERR_UNSUPPORTED; }
     int per_sm = 0;
     int grid = cg_grid_size(g.dim, g.batch, mask, &per_sm);

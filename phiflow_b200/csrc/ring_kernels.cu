@@ -568,12 +568,13 @@ struct REpiLaplace {
 
 template <class PH>
 struct REpiResidual0 {          // e0 = rhs
-    float* r; float mean, offs; float acc0, acc1; PH ph;
+    float* r; float mean, offs; float acc0, acc1; PH ph; bool tol_from_y;   // CG-adaptive: tolerance relative to |y|^2
     __device__ __forceinline__ void set_plane(int z, int nz) { ph.set_plane(z, nz); }
     __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid, const float4& y, const float4&, const float4&)
     {
         float4 rt = make_float4((y.x - mean) - q.x, (y.y - mean) - q.y, (y.z - mean) - q.z, (y.w - mean) - q.w);
         float4 rr = make_float4(rt.x - offs, rt.y - offs, rt.z - offs, rt.w - offs);
+        if (tol_from_y) rt = make_float4(y.x - mean, y.y - mean, y.z - mean, y.w - mean);
         if (nvalid == 4) {
             *reinterpret_cast<float4*>(r + off) = rr;
             if (ph.zf) ph.put4(off, rr);
@@ -598,9 +599,25 @@ struct REpiPassA {
     }
 };
 
+// CG-adaptive pass A: the second sum is d'.r (e0 = r, element-wise), _linalg.py:113
+template <class PH>
+struct REpiPassAAdapt {
+    float* dnew; float acc0, acc1; PH ph;
+    __device__ __forceinline__ void set_plane(int z, int nz) { ph.set_plane(z, nz); }
+    __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid, const float4& re, const float4&, const float4&)
+    {
+        if (nvalid == 4) {
+            *reinterpret_cast<float4*>(dnew + off) = c;
+            if (ph.zf) ph.put4(off, c);
+            acc0 += c.x * q.x + c.y * q.y + c.z * q.z + c.w * q.w;
+            acc1 += c.x * re.x + c.y * re.y + c.z * re.z + c.w * re.w;
+        } else for (int j = 0; j < nvalid; ++j) { const float v = f4_get(c, j); dnew[off + j] = v; if (ph.zf) ph.put1(off + j, v); acc0 += v * f4_get(q, j); acc1 += v * f4_get(re, j); }
+    }
+};
+
 // The solution update is applied every second iteration only: x_{k+1} = x_{k-1} + alpha_{k-1} d_{k-1} + alpha_k d_k needs
 // the previous direction (still intact in the other d buffer) but saves one read+write of x: 30 instead of 32 B/cell/it.
-template <class PH>
+template <class PH, bool RQ = false>      // RQ (CG-adaptive): the second sum is r_new . q (_linalg.py:119)
 struct REpiPassBr {             // odd iterations: e0 = r; x is left alone
     float* r; float alpha, offs; float acc0, acc1; PH ph;
     __device__ __forceinline__ void set_plane(int z, int nz) { ph.set_plane(z, nz); }
@@ -612,11 +629,12 @@ struct REpiPassBr {             // odd iterations: e0 = r; x is left alone
             *reinterpret_cast<float4*>(r + off) = rv;
             if (ph.zf) ph.put4(off, rv);
             acc0 += rv.x * rv.x + rv.y * rv.y + rv.z * rv.z + rv.w * rv.w;
-        } else for (int j = 0; j < nvalid; ++j) { const float t = f4_get(rv, j); r[off + j] = t; if (ph.zf) ph.put1(off + j, t); acc0 += t * t; }
+            if (RQ) acc1 += rv.x * q.x + rv.y * q.y + rv.z * q.z + rv.w * q.w;
+        } else for (int j = 0; j < nvalid; ++j) { const float t = f4_get(rv, j); r[off + j] = t; if (ph.zf) ph.put1(off + j, t); acc0 += t * t; if (RQ) acc1 += t * f4_get(q, j); }
     }
 };
 
-template <class PH>
+template <class PH, bool RQ = false>
 struct REpiPassB {              // even iterations: e0 = x, e1 = r, e2 = previous direction
     float* x; float* r; float alpha, aprev, offs; float acc0, acc1; PH ph;
     __device__ __forceinline__ void set_plane(int z, int nz) { ph.set_plane(z, nz); }
@@ -631,7 +649,8 @@ struct REpiPassB {              // even iterations: e0 = x, e1 = r, e2 = previou
             *reinterpret_cast<float4*>(r + off) = rv;
             if (ph.zf) ph.put4(off, rv);
             acc0 += rv.x * rv.x + rv.y * rv.y + rv.z * rv.z + rv.w * rv.w;
-        } else for (int j = 0; j < nvalid; ++j) { x[off + j] = f4_get(xv, j); const float t = f4_get(rv, j); r[off + j] = t; if (ph.zf) ph.put1(off + j, t); acc0 += t * t; }
+            if (RQ) acc1 += rv.x * q.x + rv.y * q.y + rv.z * q.z + rv.w * q.w;
+        } else for (int j = 0; j < nvalid; ++j) { x[off + j] = f4_get(xv, j); const float t = f4_get(rv, j); r[off + j] = t; if (ph.zf) ph.put1(off + j, t); acc0 += t * t; if (RQ) acc1 += t * f4_get(q, j); }
     }
 };
 
@@ -728,7 +747,7 @@ __device__ __forceinline__ void ring_unit_cells(const RingCfg& cfg, const DGrid&
         }
 }
 
-template <int DIM, bool GENERIC, bool DIST>
+template <int DIM, bool GENERIC, bool DIST, bool ADAPT>
 __global__ void __launch_bounds__(RING_THREADS, 1)
 k_cg_ring(CgRingArgs A)
 {
@@ -743,6 +762,7 @@ k_cg_ring(CgRingArgs A)
     const int batch = g.batch;
     const double cells = (double)g.n[0] * g.n[1] * g.n[2] * (A.cm.n > 1 ? A.cm.n : 1);   // global cell count (equal slabs)
     const float coffs = a.prm.matrix_offset;
+    constexpr bool adaptive = ADAPT;                 // a.prm.method == PHI_SOLVER_CG_ADAPTIVE, chosen by the launcher
     int region = 0;
     ThreadGroups tg;
     groups_init(tg, cfg, g, a.pf);
@@ -808,7 +828,7 @@ k_cg_ring(CgRingArgs A)
         const float* hsrc[2] = {a.x, nullptr};
         const float* esrc[2] = {a.rhs, nullptr};
         sweep(nullptr, [&](const RingUnit& u, float& acc0, float& acc1) {
-            REpiResidual0<PH> epi{a.r, sh.mean[u.b], sh.offs[u.b], 0.f, 0.f, peer_halo(cm.lo_r, cm.hi_r)};
+            REpiResidual0<PH> epi{a.r, sh.mean[u.b], sh.offs[u.b], 0.f, 0.f, peer_halo(cm.lo_r, cm.hi_r), adaptive};
             ring_process_unit<GENERIC, DIM, 1, 1>(rg, cfg, g, a.pf, tg, hsrc, esrc, 0.f, u, epi);
             acc0 += epi.acc0; acc1 += epi.acc1;
         });
@@ -829,11 +849,13 @@ k_cg_ring(CgRingArgs A)
     if (threadIdx.x == 0) { int any = 0; for (int b = 0; b < batch; ++b) any |= sh.cont[b]; *sh.any_cont = any; }
     __syncthreads();
 
+    // a.prm.method == PHI_SOLVER_CG_ADAPTIVE (_linalg.py:93-128) reuses both passes: pass A forms d' = r - c d (beta = -c) and
+    // sums d'.Ad' and d'.r, pass B applies the step (d'.r)/(d'.Ad') and sums |r|^2 and r.Ad' for the next c.
     float* dold = a.d0; float* dnew = a.d1;
     float* lo_dnew = cm.lo_d1; float* hi_dnew = cm.hi_d1; float* lo_dold = cm.lo_d0; float* hi_dold = cm.hi_d0;
     bool x_pending = false;      // all running entries are at the same iteration, so one flag describes them all
     while (*sh.any_cont && comm_ok) {
-        if (!(cfg.dbg & 1)) {   // pass A
+        if (cfg.dbg & 1) {} else if constexpr (!ADAPT) {   // pass A
             const float* hsrc[2] = {a.r, dold};
             const float* esrc[2] = {nullptr, nullptr};
             sweep(sh.cont, [&](const RingUnit& u, float& acc0, float& acc1) {
@@ -841,13 +863,28 @@ k_cg_ring(CgRingArgs A)
                 ring_process_unit<GENERIC, DIM, 2, 0>(rg, cfg, g, a.pf, tg, hsrc, esrc, sh.beta[u.b], u, epi);
                 acc0 += epi.acc0; acc1 += epi.acc1;
             });
+        } else {                                    // pass A of CG-adaptive: additionally d'.r (r once more, element-wise)
+            const float* hsrc[2] = {a.r, dold};
+            const float* esrc[2] = {a.r, nullptr};
+            sweep(sh.cont, [&](const RingUnit& u, float& acc0, float& acc1) {
+                REpiPassAAdapt<PH> epi{dnew, 0.f, 0.f, peer_halo(lo_dnew, hi_dnew)};
+                ring_process_unit<GENERIC, DIM, 2, 1>(rg, cfg, g, a.pf, tg, hsrc, esrc, sh.beta[u.b], u, epi);
+                acc0 += epi.acc0; acc1 += epi.acc1;
+            });
         }
         barrier_and_reduce(sh.cont);
         for (int b = threadIdx.x; b < batch; b += blockDim.x) {
             if (!sh.cont[b]) continue;
+            sh.aprev[b] = sh.alpha[b];
+            if (adaptive) {                          // step = (d.r) / (d.Ad), divide_no_nan (_linalg.py:113-114)
+                const double dq = sh.sum0[b];
+                sh.alpha[b] = (dq != 0.0) ? (float)(sh.sum1[b] / dq) : 0.f;
+                sh.delta[b] = dq;                    // kept for the direction update after pass B
+                sh.offs[b] = 0.f;
+                continue;
+            }
             const double S = sh.sum1[b];
             const double dq = sh.sum0[b] + (double)coffs * S * S;
-            sh.aprev[b] = sh.alpha[b];
             sh.alpha[b] = (dq != 0.0) ? (float)(sh.delta[b] / dq) : 0.f;
             sh.offs[b] = coffs * (float)S;
         }
@@ -856,17 +893,29 @@ k_cg_ring(CgRingArgs A)
             const float* hsrc[2] = {dnew, nullptr};
             const float* esrc[3] = {a.r, nullptr, nullptr};
             sweep(sh.cont, [&](const RingUnit& u, float& acc0, float& acc1) {
-                REpiPassBr<PH> epi{a.r, sh.alpha[u.b], sh.offs[u.b], 0.f, 0.f, peer_halo(cm.lo_r, cm.hi_r)};
-                ring_process_unit<GENERIC, DIM, 1, 1>(rg, cfg, g, a.pf, tg, hsrc, esrc, 0.f, u, epi);
-                acc0 += epi.acc0;
+                if constexpr (ADAPT) {
+                    REpiPassBr<PH, true> epi{a.r, sh.alpha[u.b], 0.f, 0.f, 0.f, peer_halo(cm.lo_r, cm.hi_r)};
+                    ring_process_unit<GENERIC, DIM, 1, 1>(rg, cfg, g, a.pf, tg, hsrc, esrc, 0.f, u, epi);
+                    acc0 += epi.acc0; acc1 += epi.acc1;
+                } else {
+                    REpiPassBr<PH> epi{a.r, sh.alpha[u.b], sh.offs[u.b], 0.f, 0.f, peer_halo(cm.lo_r, cm.hi_r)};
+                    ring_process_unit<GENERIC, DIM, 1, 1>(rg, cfg, g, a.pf, tg, hsrc, esrc, 0.f, u, epi);
+                    acc0 += epi.acc0;
+                }
             });
         } else {            // pass B, even iteration: x += alpha_prev d_prev + alpha d
             const float* hsrc[2] = {dnew, nullptr};
             const float* esrc[3] = {a.x, a.r, dold};
             sweep(sh.cont, [&](const RingUnit& u, float& acc0, float& acc1) {
-                REpiPassB<PH> epi{a.x, a.r, sh.alpha[u.b], sh.aprev[u.b], sh.offs[u.b], 0.f, 0.f, peer_halo(cm.lo_r, cm.hi_r)};
-                ring_process_unit<GENERIC, DIM, 1, 3>(rg, cfg, g, a.pf, tg, hsrc, esrc, 0.f, u, epi);
-                acc0 += epi.acc0;
+                if constexpr (ADAPT) {
+                    REpiPassB<PH, true> epi{a.x, a.r, sh.alpha[u.b], sh.aprev[u.b], 0.f, 0.f, 0.f, peer_halo(cm.lo_r, cm.hi_r)};
+                    ring_process_unit<GENERIC, DIM, 1, 3>(rg, cfg, g, a.pf, tg, hsrc, esrc, 0.f, u, epi);
+                    acc0 += epi.acc0; acc1 += epi.acc1;
+                } else {
+                    REpiPassB<PH> epi{a.x, a.r, sh.alpha[u.b], sh.aprev[u.b], sh.offs[u.b], 0.f, 0.f, peer_halo(cm.lo_r, cm.hi_r)};
+                    ring_process_unit<GENERIC, DIM, 1, 3>(rg, cfg, g, a.pf, tg, hsrc, esrc, 0.f, u, epi);
+                    acc0 += epi.acc0;
+                }
             });
         }
         x_pending = !x_pending;
@@ -874,8 +923,10 @@ k_cg_ring(CgRingArgs A)
         for (int b = threadIdx.x; b < batch; b += blockDim.x) {
             if (!sh.cont[b]) continue;
             const double dn = sh.sum0[b];
-            const double dprev = sh.delta[b];
-            sh.beta[b] = (dprev != 0.0) ? (float)(dn / dprev) : 0.f;
+            const double dprev = sh.delta[b];                 // CG: previous |r|^2;  CG-adaptive: d.Ad of this iteration
+            // CG: d' = r + (|r'|^2 / |r|^2) d;  CG-adaptive: d' = r - ((r.Ad) / (d.Ad)) d  (_linalg.py:120)
+            if (adaptive) sh.beta[b] = (dprev != 0.0) ? -(float)(sh.sum1[b] / dprev) : 0.f;
+            else sh.beta[b] = (dprev != 0.0) ? (float)(dn / dprev) : 0.f;
             sh.delta[b] = dn;
             const int it = ++sh.iters[b];
             const float rsq = fabsf((float)dn);
@@ -1051,10 +1102,13 @@ int phi_launch_cg_ring(const CgLaunch& l, const CommDev* cm, cudaStream_t s)
     cudaError_t e;
     const bool generic = !ring_all_fast(g, l.pf, A.cfg);
     const bool dist = cm && cm->n > 1;
-#define CG_RING_FN(D, GEN) (dist ? (const void*)k_cg_ring<D, GEN, true> : (const void*)k_cg_ring<D, GEN, false>)
+    const bool adapt = l.prm.method == PHI_SOLVER_CG_ADAPTIVE;
+#define CG_RING_FN2(D, GEN, DI) (adapt ? (const void*)k_cg_ring<D, GEN, DI, true> : (const void*)k_cg_ring<D, GEN, DI, false>)
+#define CG_RING_FN(D, GEN) (dist ? CG_RING_FN2(D, GEN, true) : CG_RING_FN2(D, GEN, false))
     const void* fn = g.dim == 3 ? (generic ? CG_RING_FN(3, true) : CG_RING_FN(3, false))
                                 : (generic ? CG_RING_FN(2, true) : CG_RING_FN(2, false));
 #undef CG_RING_FN
+#undef CG_RING_FN2
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem);
     if (e != cudaSuccess || per_sm < 1) return -100;

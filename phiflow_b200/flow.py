@@ -582,9 +582,10 @@ diffuse = SimpleNamespace(explicit=explicit)
 def _cg_params(v: StaggeredGrid, solve: Solve):
     # Solver policy: 'CG' is the north-star solver.  'auto' (the default Solve()) is mapped to it as well; the vendored PhiML
     # maps 'auto' to CG-adaptive (backend/_backend.py:1446-1447), which on these symmetric staggered systems reaches the same
-    # solution to the solver tolerance with different iteration counts.  An explicit 'CG-adaptive' is not on the fast path yet.
-    _require(solve.method in ('CG', 'auto'), f"solver '{solve.method}'")
-    return ops.cg_params(v.vspec, rtol=solve.rel_tol, atol=solve.abs_tol, max_iter=solve.max_iterations, matrix_offset=solve.matrix_offset)
+    # solution to the solver tolerance with different iteration counts.  An explicit 'CG-adaptive' runs the adaptive variant of the ring kernel.
+    _require(solve.method in ('CG', 'auto', 'CG-adaptive'), f"solver '{solve.method}'")
+    return ops.cg_params(v.vspec, rtol=solve.rel_tol, atol=solve.abs_tol, max_iter=solve.max_iterations, matrix_offset=solve.matrix_offset,
+                         method='CG-adaptive' if solve.method == 'CG-adaptive' else 'CG')
 
 
 def _finish_solve(dom, solve: Solve):

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in phicuda.h but not exported"
         assert name in _lib.PROTOTYPES, f"{name} has no ctypes prototype"
     assert sorted(_lib.PROTOTYPES) == names
-    assert lib.phicuda_abi_version() == 1
+    assert lib.phicuda_abi_version() == 2
 
 
 def test_struct_sizes_match_c():

@@ -280,6 +280,47 @@ def test_cg_truncated_iterates_match_oracle(vname):
             np.testing.assert_allclose(got[b], xr, rtol=0, atol=2e-5 * max(1.0, np.abs(xr).max()))
 
 
+@pytest.mark.parametrize('vname', ['open', 'mixed', 'mixed3', 'periodic3'])
+@pytest.mark.parametrize('rtol', [1e-3, 1e-5])
+def test_cg_adaptive_matches_oracle(vname, rtol):
+    """Solve('CG-adaptive') (_linalg.py:93-128; what Solve('auto') runs in PhiML 1.7): same iterates as the oracle restatement,
+    which is pinned against the vendored PhiML in tests/golden/phiml_cg_adaptive.npz."""
+    vbc = ALL_V[vname]
+    d = len(vbc)
+    rng = np.random.default_rng(9)
+    res = (40, 24) if d == 2 else (20, 12, 10)
+    dx = dx_of(d)
+    batch = 2
+    dom = ops.Domain(res, dx, batch, vbc=vbc)
+    rhs = rng.standard_normal((batch,) + res).astype(np.float32)
+    rhs[1] *= 5.0
+    A = O.poisson_matrix(res, dx, O.pressure_bc(vbc))
+    rank_def = not O.is_flexible(vbc)
+    prm = ops.cg_params(vbc, rtol=rtol, atol=1e-5, max_iter=1000, method='CG-adaptive')
+    got = dom.centered_to_numpy(ops.cg_poisson(dom, vbc, dom.centered_from_numpy(rhs), None, prm), squeeze=False)
+    info = ops.read_results(dom)
+    for b in range(batch):
+        y = rhs[b] - rhs[b].mean() if rank_def else rhs[b]
+        ref = O.cg_adaptive(A, y, np.zeros(res, np.float32), rtol, 1e-5, 1000, None)
+        assert info['converged'][b] == int(ref['converged']) and info['diverged'][b] == 0
+        assert abs(int(info['iterations'][b]) - ref['iterations']) <= max(2, ref['iterations'] // 10), (info['iterations'][b], ref['iterations'])
+        xr = ref['x'].reshape(res)
+        if rank_def:
+            xr = xr - xr.mean()
+        np.testing.assert_allclose(got[b], xr, rtol=0, atol=20 * rtol * np.abs(xr).max())
+    # truncated iterates, odd and even counts (deferred x update)
+    for k in (1, 2, 3):
+        prm = ops.cg_params(vbc, rtol=1e-12, atol=0.0, max_iter=k, method='CG-adaptive')
+        got = dom.centered_to_numpy(ops.cg_poisson(dom, vbc, dom.centered_from_numpy(rhs), None, prm), squeeze=False)
+        for b in range(batch):
+            y = rhs[b] - rhs[b].mean() if rank_def else rhs[b]
+            ref = O.cg_adaptive(A, y, np.zeros(res, np.float32), 1e-12, 0.0, k, None)
+            xr = ref['x'].reshape(res)
+            if rank_def:
+                xr = xr - xr.mean()
+            np.testing.assert_allclose(got[b], xr, rtol=0, atol=2e-5 * max(1.0, np.abs(xr).max()))
+
+
 def test_cg_matrix_offset_matches_reference_formulation():
     """With the rank-1 offset c of _optimize.py:705-714 the iterates follow the reference's (A + c 11^T) system."""
     vbc = BCS3['periodic3']
