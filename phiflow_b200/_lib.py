@@ -108,7 +108,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.phicuda_abi_version() != 1:
+    if lib.phicuda_abi_version() != 2:
         raise RuntimeError("libphicuda ABI version mismatch")
     _lib = lib
     return lib
