@@ -277,6 +277,7 @@ def main():
     ap.add_argument('--size', type=int, default=512)
     ap.add_argument('--cpu-size', type=int, default=96, dest='cpu_size')
     ap.add_argument('--no-cpu', action='store_true', dest='no_cpu')
+    ap.add_argument('--halo', type=int, default=16, help='z-slab halo planes allocated per side (N>1); grows on demand')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != 'reference' else args.warmup
     if args.impl == 'reference':

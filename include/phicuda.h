@@ -102,6 +102,29 @@ size_t      phicuda_last_error(char* buf, size_t buf_len);
 /* Name, SM count and compute capability of the current device; returns 0 or a cudaError_t. */
 int         phicuda_device_info(char* name, size_t name_len, int* sm_count, int* cc_major, int* cc_minor);
 
+/* Diagnostics: which kernel variant the calling thread's most recent laplace / CG launch selected.  The parity tests use
+ * it to assert that a case really ran on the instantiation it was written for (e.g. the branch-free TMA-ring variant that
+ * bench.py times) instead of silently taking another path. */
+#define PHI_KERNEL_NONE          0
+#define PHI_KERNEL_LAPLACE_RING  1   /* k_laplace_ring  (TMA ring) */
+#define PHI_KERNEL_LAPLACE_MARCH 2   /* k_laplace       (register marching) */
+#define PHI_KERNEL_CG_RING       3   /* k_cg_ring       (persistent, TMA ring) */
+#define PHI_KERNEL_CG_MARCH      4   /* k_cg_poisson    (persistent, register marching) */
+#define PHI_KERNEL_STENCIL_RING  5   /* k_div_ring / k_gradsub_ring / k_advect_ring: see `stencil` */
+typedef struct PhiLaunchInfo {
+    int32_t kernel;        /* PHI_KERNEL_* */
+    int32_t generic;       /* 1: variant with per-tile boundary handling, 0: branch-free variant (every tile qualifies) */
+    int32_t dist;          /* 1: multi-GPU instantiation (peer halo stores + in-kernel all-reduce) */
+    int32_t adaptive;      /* 1: CG-adaptive */
+    int32_t masked;        /* 1: obstacle mask variant */
+    int32_t TY, stages;    /* tile height (grid lines), ring depth */
+    int32_t ZC, nzc;       /* planes per unit, z chunks */
+    int32_t groups;        /* float4 groups per consumer thread and plane */
+    int32_t total_units;   /* units of the whole launch */
+    int32_t grid_ctas;     /* CTAs launched (units per CTA = ceil(total_units / grid_ctas)) */
+} PhiLaunchInfo;
+int phicuda_last_launch_info(PhiLaunchInfo* out);
+
 /* ---- A7  field.laplace order 2 (phi/field/_field_math.py:118-145 -> PhiML/phiml/math/_nd.py:825-861) ------------- */
 /* y = sum_d (x[i-1] + x[i+1] - 2 x[i]) / dx_d^2, ghost cells from `bc`.  8 B/cell. */
 int phicuda_laplace_f32(const PhiGrid* g, const PhiBC* bc, const float* x, float* y, void* stream);
@@ -135,6 +158,11 @@ int phicuda_axpy_centered_f32(const PhiGrid* g, float a, const float* x, float* 
 /* v_c += dt * resample(s * b_c, to=faces of c)  (sample_grid_at_faces, phi/field/_resample.py:272-276). */
 int phicuda_add_buoyancy_f32(const PhiGrid* g, const PhiVBC* vbc, const PhiBC* sbc, const float* s,
                              const float b[3], float dt, float* const v[3], void* stream);
+
+/* out[c] = max |v_c| over the stored faces of the owned planes, c < dim (out: 3 floats on the device).  The semi-Lagrangian
+ * back-trace is unbounded in the reference (phi/physics/advect.py:20-24); z-slab runs size the advection halo
+ * h = ceil(max|v_z| dt / dz) + 1 from it before every step.  NaN is reported as +inf. */
+int phicuda_max_abs_velocity_f32(const PhiGrid* g, const PhiVBC* vbc, const float* const v[3], float* out, void* stream);
 
 /* ---- A2 + A12  pressure solve: CG on the matrix-free Poisson operator ------------------------------------------
  * Replaces math.solve_linear(masked_laplace, div, Solve('CG', ...)) (phi/physics/fluid.py:156,

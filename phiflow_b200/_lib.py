@@ -38,6 +38,14 @@ class PhiCgResult(C.Structure):
                 ('residual_sq', C.c_float), ('tol_sq', C.c_float), ('initial_residual_sq', C.c_float)]
 
 
+class PhiLaunchInfo(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ('kernel', 'generic', 'dist', 'adaptive', 'masked', 'TY', 'stages', 'ZC', 'nzc', 'groups',
+                                         'total_units', 'grid_ctas')]
+
+
+KERNEL_NONE, KERNEL_LAPLACE_RING, KERNEL_LAPLACE_MARCH, KERNEL_CG_RING, KERNEL_CG_MARCH, KERNEL_STENCIL_RING = range(6)
+
+
 class PhiPlumeParams(C.Structure):
     _fields_ = [('dt', C.c_float), ('inflow_rate', C.c_float), ('buoyancy', C.c_float * 3), ('mac_cormack', C.c_int32)]
 
@@ -50,6 +58,8 @@ PROTOTYPES = {
     'phicuda_abi_version': (C.c_int, []),
     'phicuda_last_error': (C.c_size_t, [C.c_char_p, C.c_size_t]),
     'phicuda_device_info': (C.c_int, [C.c_char_p, C.c_size_t, _P(C.c_int), _P(C.c_int), _P(C.c_int)]),
+    'phicuda_last_launch_info': (C.c_int, [_P(PhiLaunchInfo)]),
+    'phicuda_max_abs_velocity_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), F3, C.c_void_p, C.c_void_p]),
     'phicuda_laplace_f32': (C.c_int, [_P(PhiGrid), _P(PhiBC), C.c_void_p, C.c_void_p, C.c_void_p]),
     'phicuda_laplace_axpy_f32': (C.c_int, [_P(PhiGrid), _P(PhiBC), C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     'phicuda_divergence_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), F3, C.c_void_p, C.c_void_p]),

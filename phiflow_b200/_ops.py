@@ -265,6 +265,22 @@ def add_buoyancy(dom: Domain, vbc, sbc, s, factor: Sequence[float], dt: float, v
     return v
 
 
+def max_abs_velocity(dom: Domain, vbc, v, out: torch.Tensor = None) -> torch.Tensor:
+    """Device tensor of 3 floats: max |v_c| per component over the stored faces of the owned planes (CFL number of the
+    unbounded semi-Lagrangian back-trace, phi/physics/advect.py:20-24)."""
+    require_cuda()
+    out = torch.zeros(3, dtype=torch.float32, device=dom.device) if out is None else out
+    _lib.check(_lib.load().phicuda_max_abs_velocity_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(v, dom.foff), _ptr(out), _stream()))
+    return out
+
+
+def last_launch_info() -> dict:
+    """Which kernel variant this thread's most recent laplace / CG launch selected (include/phicuda.h PhiLaunchInfo)."""
+    info = _lib.PhiLaunchInfo()
+    _lib.check(_lib.load().phicuda_last_launch_info(C.byref(info)))
+    return {k: int(getattr(info, k)) for k, _ in _lib.PhiLaunchInfo._fields_}
+
+
 def _is_flexible(vspec) -> bool:
     spec = vspec[0] if isinstance(vspec, list) else vspec
     return any(side == ZG for ax in spec for side in ax)

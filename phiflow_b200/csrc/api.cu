@@ -16,6 +16,9 @@ void phi_set_error(const char* fmt, ...)
     va_end(ap);
 }
 
+static thread_local PhiLaunchInfo g_last_launch = {};
+void phi_note_launch(const PhiLaunchInfo& info) { g_last_launch = info; }
+
 bool phi_ring_enabled()
 {
     const char* v = getenv("PHICUDA_NO_RING");       // diagnostics: force the register-marching kernels
@@ -172,6 +175,13 @@ size_t phicuda_last_error(char* buf, size_t buf_len)
     return n;
 }
 
+int phicuda_last_launch_info(PhiLaunchInfo* out)
+{
+    if (!out) { phi_set_error("last_launch_info: out is NULL"); return PHI_ERR_INVALID; }
+    *out = g_last_launch;
+    return 0;
+}
+
 int phicuda_device_info(char* name, size_t name_len, int* sm_count, int* cc_major, int* cc_minor)
 {
     int dev = 0;
@@ -270,6 +280,14 @@ int phicuda_add_buoyancy_f32(const PhiGrid* g, const PhiVBC* vbc, const PhiBC* s
     if (!s || !b) { phi_set_error("add_buoyancy: NULL argument"); return PHI_ERR_INVALID; }
     for (int c = 0; c < 3; ++c) out.p[c] = c < g->dim ? v[c] : nullptr;
     return cuda_fail(phi_launch_buoyancy(dg, dv, out, sf, s, b, dt, (cudaStream_t)stream), "add_buoyancy");
+}
+
+int phicuda_max_abs_velocity_f32(const PhiGrid* g, const PhiVBC* vbc, const float* const v[3], float* out, void* stream)
+{
+    DGrid dg; DVec dv;
+    CHECK(phi_make_dgrid(g, &dg)); CHECK(make_vec(g, vbc, v, &dv));
+    if (!out) { phi_set_error("max_abs_velocity: out is NULL"); return PHI_ERR_INVALID; }
+    return cuda_fail(phi_launch_absmax(dg, dv, out, (cudaStream_t)stream), "max_abs_velocity");
 }
 
 // ---- N4: static obstacles ------------------------------------------------------------------------------------------------

@@ -9,6 +9,7 @@ int phi_launch_grad_sub(const DGrid& g, const DVec& vin, const DVecOut& v, const
 int phi_launch_mul_faces(const DGrid& g, const DVec& vin, const DVecOut& v, const float* const mask[3], cudaStream_t s);
 int phi_launch_buoyancy(const DGrid& g, const DVec& vin, const DVecOut& v, const DField& sf, const float* sarr,
                         const float b[3], float dt, cudaStream_t s);
+int phi_launch_absmax(const DGrid& g, const DVec& v, float* out, cudaStream_t s);
 int phi_launch_axpy(const DGrid& g, const DField& cf, float a, const float* x, float* y, cudaStream_t s);
 
 // target_comp < 0: centred field

@@ -320,3 +320,4 @@ int phi_make_component(const PhiGrid* g, const PhiBC* bc, int c, DField* out);
 int phi_pressure_bc(const PhiVBC* vbc, int dim, PhiBC* out);
 UnitMap phi_make_unit_map(const DGrid& g, int target_units);
 void phi_set_error(const char* fmt, ...);
+void phi_note_launch(const PhiLaunchInfo& info);

@@ -1055,6 +1055,14 @@ static bool ring_all_fast(const DGrid& g, const DField& f, const RingCfg& c)
     return c.groups == 1 || c.groups == 2 || c.groups == 4;
 }
 
+static void note_ring_launch(int kernel, const RingCfg& c, bool generic, bool dist, bool adaptive, int grid)
+{
+    PhiLaunchInfo li; memset(&li, 0, sizeof(li));
+    li.kernel = kernel; li.generic = generic; li.dist = dist; li.adaptive = adaptive;
+    li.TY = c.TY; li.stages = c.R; li.ZC = c.ZC; li.nzc = c.nzc; li.groups = c.groups; li.total_units = c.total_units; li.grid_ctas = grid;
+    phi_note_launch(li);
+}
+
 static int sm_count()
 {
     int dev = 0, sms = 0;
@@ -1084,6 +1092,7 @@ int phi_launch_laplace_ring(const DGrid& g, const DField& f, const float* x, flo
 #undef LAUNCH_LAP2
 #undef LAUNCH_LAP
     if (e != cudaSuccess) return (int)e;
+    note_ring_launch(PHI_KERNEL_LAPLACE_RING, cfg, generic, false, false, grid);
     return (int)cudaGetLastError();
 }
 
@@ -1129,5 +1138,6 @@ int phi_launch_cg_ring(const CgLaunch& l, const CommDev* cm, cudaStream_t s)
     void* args[] = {&A};
     e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, smem, s);
     if (e != cudaSuccess) { phi_set_error("cg ring: cooperative launch failed: %s", cudaGetErrorString(e)); return (int)e; }
+    note_ring_launch(PHI_KERNEL_CG_RING, A.cfg, generic, dist, adapt, grid);
     return 0;
 }

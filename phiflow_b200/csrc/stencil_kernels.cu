@@ -48,6 +48,8 @@ int phi_launch_laplace(const DGrid& g, const DField& f, const float* x, float* y
         if (axpy) k_laplace<2, true><<<blocks, block, 0, s>>>(g, f, um, x, y, coeff);
         else      k_laplace<2, false><<<blocks, block, 0, s>>>(g, f, um, x, y, coeff);
     }
+    PhiLaunchInfo li = {}; li.kernel = PHI_KERNEL_LAPLACE_MARCH; li.generic = 1; li.total_units = um.total_units; li.grid_ctas = blocks;
+    phi_note_launch(li);
     return (int)cudaGetLastError();
 }
 
@@ -208,5 +210,59 @@ int phi_launch_axpy(const DGrid& g, const DField& cf, float a, const float* x, f
 {
     if (g.dim == 3) k_axpy<3><<<scalar_grid(g), 128, 0, s>>>(g, cf, a, x, y);
     else            k_axpy<2><<<scalar_grid(g), 128, 0, s>>>(g, cf, a, x, y);
+    return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// max |v_c| per component over the stored faces (owned planes only).  The semi-Lagrangian back-trace reaches
+// ceil(max|v_z| dt / dz) + 1 planes into the neighbouring slab (phi/physics/advect.py:20-24, 156-179: the reference's
+// lookup is unbounded), so the z-slab driver sizes its halo exchange from this number before every step.
+// Non-negative floats order like their bit patterns -> atomicMax on unsigned.
+// ---------------------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(256)
+k_absmax(DGrid g, DVec v, unsigned* __restrict__ out)
+{
+    __shared__ float red[8];
+    const int nx4 = g.fext[0] / 4;
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) {
+        const DField& f = v.f[c];
+        const int ny = f.hi[1] - f.lo[1] + 1, nz = DIM == 3 ? f.hi[2] - f.lo[2] + 1 : 1;
+        const long long total = (long long)g.batch * nz * ny * nx4;
+        float m = 0.f;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const int x4 = (int)(i % nx4); long long r = i / nx4;
+            const int y = (int)(r % ny) + f.lo[1]; r /= ny;
+            const int z = DIM == 3 ? (int)(r % nz) + f.lo[2] : 0; const int b = (int)(r / nz);
+            const float4 q = *reinterpret_cast<const float4*>(v.p[c] + (long long)b * f.sb + (long long)z * f.sz + (long long)y * f.sy + 4 * x4);
+            const int x0 = 4 * x4;
+            if (x0 + 0 >= f.lo[0] && x0 + 0 <= f.hi[0]) m = fmaxf(m, fabsf(q.x));
+            if (x0 + 1 >= f.lo[0] && x0 + 1 <= f.hi[0]) m = fmaxf(m, fabsf(q.y));
+            if (x0 + 2 >= f.lo[0] && x0 + 2 <= f.hi[0]) m = fmaxf(m, fabsf(q.z));
+            if (x0 + 3 >= f.lo[0] && x0 + 3 <= f.hi[0]) m = fmaxf(m, fabsf(q.w));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+            if (!(m == m)) m = __int_as_float(0x7f800000);          // NaN -> +inf: "halo cannot be bounded"
+            atomicMax(out + c, __float_as_uint(m));
+        }
+        __syncthreads();
+    }
+}
+
+int phi_launch_absmax(const DGrid& g, const DVec& v, float* out, cudaStream_t s)
+{
+    cudaError_t e = cudaMemsetAsync(out, 0, 3 * sizeof(float), s);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g.dim == 3) k_absmax<3><<<sms * 8, 256, 0, s>>>(g, v, reinterpret_cast<unsigned*>(out));
+    else            k_absmax<2><<<sms * 8, 256, 0, s>>>(g, v, reinterpret_cast<unsigned*>(out));
     return (int)cudaGetLastError();
 }

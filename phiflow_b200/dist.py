@@ -9,6 +9,7 @@ persistent kernel per rank that exchanges halo planes and dot products through N
 Batched 2-D runs shard the batch axis instead - entries are independent systems, no communication at all.
 """
 import ctypes as C
+import math
 from typing import List, Sequence
 
 import torch
@@ -45,6 +46,27 @@ def batch_shard(total_batch: int, rank: int = None, world: int = None):
     return first, base + (1 if rank < rem else 0)
 
 
+def advection_halo(max_abs_vz: float, dt: float, dz: float, bc_const_max: float = 0.0) -> int:
+    """Halo planes the semi-Lagrangian passes of one step need: h = ceil(max|v_z| * |dt| / dz) + 1.
+    The reference's back-trace `points - dt * v(points)` is unbounded (phi/physics/advect.py:20-24, 156-179); the sample at
+    z - disp reads the planes floor(z - disp) and floor(z - disp) + 1, and the velocity at a face centre is an average of
+    stored values and boundary constants, hence bounded by max(max|v_z|, |constants|).  Non-finite input -> ValueError."""
+    vmax = max(float(max_abs_vz), float(bc_const_max))
+    if not math.isfinite(vmax):
+        raise ValueError("velocity is not finite: the advection halo cannot be bounded")
+    disp = vmax * abs(float(dt)) / float(dz)
+    return int(math.ceil(disp * (1.0 + 1e-6))) + 1
+
+
+class HaloTooWide(_lib.Unsupported):
+    """The back-trace reaches further than one neighbouring slab (h > planes per rank): outside the z-slab fast path."""
+
+    def __init__(self, need, have):
+        RuntimeError.__init__(self, f"semi-Lagrangian back-trace needs {need} halo planes but a slab has only {have} planes; "
+                                    f"use fewer ranks or a smaller dt (PHI_ERR_UNSUPPORTED: raised BEFORE the step computes)")
+        self.code = _lib.ERR_UNSUPPORTED
+
+
 class Slab:
     """Geometry + communication of one rank's z-slab."""
 
@@ -56,10 +78,10 @@ class Slab:
         nx, ny, nz = global_res
         assert nz % self.world == 0, f"nz={nz} must be divisible by the number of ranks {self.world}"
         self.global_res = tuple(global_res)
+        self.dx = tuple(float(h) for h in dx)
         self.nz = nz // self.world
         self.z0 = self.rank * self.nz
-        self.halo = halo if self.world > 1 else 0
-        assert self.halo <= self.nz, "halo wider than the slab"
+        self.halo = min(halo, self.nz) if self.world > 1 else 0      # allocated planes per side = widest possible exchange
         self.vbc_global = vbc
         self.vbc = local_bc(vbc, self.rank, self.world)
         spec = vbc[0] if isinstance(vbc, list) else vbc
@@ -68,37 +90,50 @@ class Slab:
         self.upper = None if self.world == 1 else ((self.rank + 1) % self.world if (periodic or self.rank < self.world - 1) else None)
         self.dom = ops.Domain((nx, ny, self.nz), dx, 1, vbc=self.vbc, device=device, halo=self.halo)
         self._comm = None
+        # largest |constant| of the z component's boundary (enters face-centre averages next to walls)
+        zspec = (vbc[2] if isinstance(vbc, list) else vbc)
+        self.bc_const_max = max([abs(float(side)) for ax in zspec for side in ax if not isinstance(side, str)] + [0.0])
 
     def bc(self, spec):
         return local_bc(spec, self.rank, self.world)
 
     # ---- halo exchange --------------------------------------------------------------------------------------------
     def exchange(self, tensors: List[torch.Tensor], width: int):
-        """Fills `width` halo planes on both sides of every tensor from the neighbouring slabs."""
+        """Fills `width` halo planes on both sides of every tensor from the neighbouring slabs.  z planes are contiguous
+        (DESIGN.md section 2), so with batch 1 the owned edge planes are sent and the halo planes received in place - no
+        staging copies; batched tensors go through contiguous staging buffers."""
         if self.world == 1:
             return
         H, nz = self.halo, self.nz
-        assert 1 <= width <= H
+        if not 1 <= width <= H:
+            raise ValueError(f"halo exchange of {width} planes but {H} are allocated")
         ops_ = []
-        recv_views = []
+        copy_back = []
+
+        def send(view, peer):
+            ops_.append(dist.P2POp(dist.isend, view if view.is_contiguous() else view.contiguous(), peer, self.group))
+
+        def recv(view, peer):
+            if view.is_contiguous():
+                ops_.append(dist.P2POp(dist.irecv, view, peer, self.group))
+            else:
+                buf = torch.empty_like(view, memory_format=torch.contiguous_format)
+                ops_.append(dist.P2POp(dist.irecv, buf, peer, self.group))
+                copy_back.append((view, buf))
         for t in tensors:
             # order matters when lower == upper (two ranks, periodic): sends and receives pair up in issue order
             if self.upper is not None:
-                ops_.append(dist.P2POp(dist.isend, t[:, H + nz - width:H + nz].contiguous(), self.upper, self.group))
+                send(t[:, H + nz - width:H + nz], self.upper)
             if self.lower is not None:
-                ops_.append(dist.P2POp(dist.isend, t[:, H:H + width].contiguous(), self.lower, self.group))
+                send(t[:, H:H + width], self.lower)
         for t in tensors:
             if self.lower is not None:
-                buf = torch.empty_like(t[:, H - width:H])
-                ops_.append(dist.P2POp(dist.irecv, buf, self.lower, self.group))
-                recv_views.append((t[:, H - width:H], buf))
+                recv(t[:, H - width:H], self.lower)
             if self.upper is not None:
-                buf = torch.empty_like(t[:, H + nz:H + nz + width])
-                ops_.append(dist.P2POp(dist.irecv, buf, self.upper, self.group))
-                recv_views.append((t[:, H + nz:H + nz + width], buf))
+                recv(t[:, H + nz:H + nz + width], self.upper)
         for req in dist.batch_isend_irecv(ops_):
             req.wait()
-        for view, buf in recv_views:
+        for view, buf in copy_back:
             view.copy_(buf)
 
     # ---- distributed pressure solve -----------------------------------------------------------------------------------
@@ -138,25 +173,82 @@ class Slab:
 
     def close(self):
         if self._comm is not None:
+            torch.cuda.synchronize(self.dom.device)
             _lib.load().phicuda_comm_destroy(self._comm)
             self._comm = None
 
 
 class SlabPlume:
-    """incompressible_step on z-slabs.  State lives on the device of each rank."""
+    """incompressible_step on z-slabs.  State lives on the device of each rank.
+
+    Advection halo: before every step the ranks agree on max|v_z| (device reduction + all_reduce(MAX)) and exchange
+    h = ceil(max|v_z| dt / dz) + 1 planes of v and s (`advection_halo`).  When h exceeds the allocated planes the state is
+    re-allocated with a wider halo (collective, all ranks take the same decision); when it exceeds the slab thickness the
+    step raises HaloTooWide BEFORE any kernel runs.  `halo_used` / `max_displacement` record the largest values seen."""
 
     def __init__(self, slab: Slab, sbc, dt, inflow_rate, buoyancy, prm, adv_halo=None):
         self.slab, self.dom = slab, slab.dom
+        self.sbc_global = sbc
         self.vbc, self.sbc = slab.vbc, slab.bc(sbc)
         self.dt, self.inflow_rate, self.buoyancy, self.prm = dt, inflow_rate, buoyancy, prm
-        self.adv_halo = adv_halo if adv_halo is not None else slab.halo
+        self.fixed_adv_halo = adv_halo            # diagnostics only: force a width instead of the CFL-derived one
         d = self.dom
         self.v, self.v2 = d.alloc_faces(), d.alloc_faces()
         self.s, self.s2 = d.alloc_centered(), d.alloc_centered()
         self.p, self.div = d.alloc_centered(), d.alloc_centered()
         self.inflow = d.alloc_centered()
-        self.launches_per_step = 9
+        self._vmax = torch.zeros(3, dtype=torch.float32, device=d.device)
+        self.launches_per_step = 10
+        self.halo_used = 0
+        self.max_displacement = 0.0
+        self.regrown = 0
 
+    # ---- halo sizing ------------------------------------------------------------------------------------------------
+    def required_halo(self) -> int:
+        """Collective: planes the advection of the coming step reads beyond the slab (same value on every rank)."""
+        s, d = self.slab, self.dom
+        if d.device.type == 'cuda':
+            ops.max_abs_velocity(d, self.vbc, self.v, out=self._vmax)
+        else:                                       # host-logic tests (gloo): same reduction with torch
+            H, nz = s.halo, s.nz
+            self._vmax.copy_(torch.stack([c[:, H:H + nz + 1].abs().max() for c in self.v]))
+        if s.world > 1:
+            dist.all_reduce(self._vmax, op=dist.ReduceOp.MAX, group=s.group)
+        vz = float(self._vmax[2].item())            # the one host round trip of the step: the width decides what is exchanged
+        h = advection_halo(vz, self.dt, s.dx[2], s.bc_const_max)
+        self.max_displacement = max(self.max_displacement, max(vz, s.bc_const_max) * abs(self.dt) / s.dx[2])
+        return h
+
+    def ensure_halo(self, h: int):
+        s = self.slab
+        if s.world == 1 or h <= s.halo:
+            return
+        if h > s.nz:
+            raise HaloTooWide(h, s.nz)
+        self._regrow(min(s.nz, max(h, 2 * s.halo)))
+
+    def _regrow(self, new_halo: int):
+        """Re-allocates the state with `new_halo` planes per side, keeping the owned planes (collective)."""
+        old, oH, nz = self.slab, self.slab.halo, self.slab.nz
+        old.close()
+        slab = Slab(old.global_res, old.dx, old.vbc_global, halo=new_halo, device=old.dom.device, group=old.group)
+        nH, d = slab.halo, slab.dom
+
+        def move(t, alloc):
+            n = alloc()
+            keep = t.shape[1] - 2 * oH               # owned planes (+ the stored upper boundary face plane, if any)
+            n[:, nH:nH + keep] = t[:, oH:oH + keep]
+            return n
+        self.v = [move(t, lambda: d.alloc_faces()[0]) for t in self.v]
+        self.v2 = d.alloc_faces()
+        self.s, self.s2 = move(self.s, d.alloc_centered), d.alloc_centered()
+        self.p, self.div = move(self.p, d.alloc_centered), d.alloc_centered()
+        self.inflow = move(self.inflow, d.alloc_centered)
+        self.slab, self.dom = slab, d
+        self.vbc, self.sbc = slab.vbc, slab.bc(self.sbc_global)
+        self.regrown += 1
+
+    # ---- the step -----------------------------------------------------------------------------------------------------
     def project(self):
         s = self.slab
         s.exchange(self.v, 1)
@@ -167,9 +259,12 @@ class SlabPlume:
         ops.grad_sub(self.dom, self.vbc, self.v, self.p)
 
     def step(self, cg_events=None):
+        if self.slab.world > 1:
+            h = self.required_halo() if self.fixed_adv_halo is None else self.fixed_adv_halo
+            self.ensure_halo(h)                    # may re-allocate; raises HaloTooWide before anything is computed
+            self.halo_used = max(self.halo_used, h)
+            self.slab.exchange(self.v + [self.s], h)
         s, d = self.slab, self.dom
-        if s.world > 1:
-            s.exchange(self.v + [self.s], self.adv_halo)
         ops.advect_centered(d, self.vbc, self.v, self.sbc, self.s, self.dt, out=self.s2)
         ops.axpy_centered(d, self.inflow_rate, self.inflow, self.s2)
         ops.advect_staggered(d, self.vbc, self.v, self.vbc, self.v, self.dt, out=self.v2)

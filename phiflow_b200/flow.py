@@ -209,8 +209,10 @@ class SolveTape:
         _TAPES.remove(self)
 
     def __getitem__(self, solve):
+        if isinstance(solve, int):                 # tape[i] / tape[-1]: records in the order the solves ran (_optimize.py:300-318)
+            return self.records[solve][1]
         for s, info in self.records:
-            if s is solve or solve in (0, -1):
+            if s is solve:
                 return info
         raise KeyError(solve)
 
@@ -579,13 +581,15 @@ diffuse = SimpleNamespace(explicit=explicit)
 # ----------------------------------------------------------------------------------------------------------------------
 # fluid  (phi/physics/fluid.py)
 # ----------------------------------------------------------------------------------------------------------------------
-def _cg_params(v: StaggeredGrid, solve: Solve):
-    # Solver policy: 'CG' is the north-star solver.  'auto' (the default Solve()) is mapped to it as well; the vendored PhiML
-    # maps 'auto' to CG-adaptive (backend/_backend.py:1446-1447), which on these symmetric staggered systems reaches the same
-    # solution to the solver tolerance with different iteration counts.  An explicit 'CG-adaptive' runs the adaptive variant of the ring kernel.
+def _cg_params(v: StaggeredGrid, solve: Solve, masked=False):
+    # Solver policy = the reference's: 'CG' is Shewchuk CG (the north-star solver); 'auto' (the default Solve()) and
+    # 'CG-adaptive' run the Hestenes-Stiefel variant exactly as the vendored PhiML maps them (backend/_backend.py:1446-1447,
+    # _linalg.py:93-128), tolerance relative to |rhs|^2.  Exception: with obstacle masks the adaptive variant is not
+    # available (it lives on the TMA ring kernel only), so 'auto' runs plain CG there and an explicit 'CG-adaptive' raises.
     _require(solve.method in ('CG', 'auto', 'CG-adaptive'), f"solver '{solve.method}'")
-    return ops.cg_params(v.vspec, rtol=solve.rel_tol, atol=solve.abs_tol, max_iter=solve.max_iterations, matrix_offset=solve.matrix_offset,
-                         method='CG-adaptive' if solve.method == 'CG-adaptive' else 'CG')
+    adaptive = solve.method == 'CG-adaptive' or (solve.method == 'auto' and not masked)
+    return ops.cg_params(v.vspec, rtol=solve.rel_tol, atol=solve.abs_tol, max_iter=solve.max_iterations,
+                         matrix_offset=0.0 if adaptive else solve.matrix_offset, method='CG-adaptive' if adaptive else 'CG')
 
 
 def _finish_solve(dom, solve: Solve):
@@ -627,19 +631,20 @@ def make_incompressible(velocity: StaggeredGrid, obstacles=(), solve: Solve = No
     solve = solve or Solve()
     _require(isinstance(velocity, StaggeredGrid), "CenteredGrid velocities")
     _require(active is None and order == 2, "active masks / higher order")
+    if solve.x0 is not None:
+        _require(isinstance(solve.x0, CenteredGrid) and solve.x0.res == velocity.res and solve.x0.batch == velocity.batch, "x0 on a different grid")
     if obstacles:
         accessible, factors = _obstacle_masks(velocity, obstacles)
         res = dict(zip(velocity.axes, velocity.res))
         p_data = solve.x0.data.clone() if solve.x0 is not None else velocity.dom.alloc_centered()
         v_data = [c.clone() for c in velocity.data]
         ops.mul_faces(velocity.dom, velocity.vspec, v_data, factors)             # apply_boundary_conditions
-        ops.make_incompressible(velocity.dom, velocity.vspec, v_data, p_data, _cg_params(velocity, solve), accessible=accessible)
+        ops.make_incompressible(velocity.dom, velocity.vspec, v_data, p_data, _cg_params(velocity, solve, masked=True), accessible=accessible)
         _finish_solve(velocity.dom, solve)
         pressure = CenteredGrid(boundary=_pressure_boundary(velocity.boundary), bounds=velocity.bounds, batch=velocity.batch, _data=p_data, **res)
         return velocity.with_values(v_data), pressure
     res = dict(zip(velocity.axes, velocity.res))
     if solve.x0 is not None:
-        _require(isinstance(solve.x0, CenteredGrid) and solve.x0.res == velocity.res, "x0 on a different grid")
         p_data = solve.x0.data.clone()
     else:
         p_data = velocity.dom.alloc_centered()

@@ -38,8 +38,8 @@ def test_struct_sizes_match_c():
     #include <stdio.h>
     #include "phicuda.h"
     int main(void) {
-        printf("%zu %zu %zu %zu %zu %zu\n", sizeof(PhiGrid), sizeof(PhiBC), sizeof(PhiVBC), sizeof(PhiCgParams),
-               sizeof(PhiCgResult), sizeof(PhiPlumeParams));
+        printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(PhiGrid), sizeof(PhiBC), sizeof(PhiVBC), sizeof(PhiCgParams),
+               sizeof(PhiCgResult), sizeof(PhiPlumeParams), sizeof(PhiLaunchInfo));
         return 0;
     }'''
     with tempfile.TemporaryDirectory() as tmp:
@@ -49,7 +49,7 @@ def test_struct_sizes_match_c():
             f.write(src)
         subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), c, '-o', exe])
         sizes = [int(v) for v in subprocess.check_output([exe]).split()]
-    mirrors = [_lib.PhiGrid, _lib.PhiBC, _lib.PhiVBC, _lib.PhiCgParams, _lib.PhiCgResult, _lib.PhiPlumeParams]
+    mirrors = [_lib.PhiGrid, _lib.PhiBC, _lib.PhiVBC, _lib.PhiCgParams, _lib.PhiCgResult, _lib.PhiPlumeParams, _lib.PhiLaunchInfo]
     assert sizes == [C.sizeof(m) for m in mirrors]
 
 

@@ -105,3 +105,87 @@ def test_local_bc_single_rank_is_identity():
     assert local_bc(spec, 0, 4)[2] == ('zg', 'halo')
     assert local_bc(spec, 3, 4)[2] == ('halo', 0.0)
     assert local_bc([spec, spec, spec], 3, 4)[1][2] == ('halo', 0.0)
+
+
+def test_advection_halo_rule():
+    """h = ceil(max|v_z| dt / dz) + 1; the reference's back-trace is unbounded (advect.py:20-24)."""
+    from phiflow_b200.dist import advection_halo
+    assert advection_halo(0.0, 0.5, 1.0) == 1
+    assert advection_halo(0.1, 0.5, 100.0 / 512) == 2            # 0.256 cells
+    assert advection_halo(1.95, 0.5, 100.0 / 512) == 6           # 4.99 cells -> 5 + 1
+    assert advection_halo(2.0, 0.5, 100.0 / 512) == 7            # 5.12 cells -> 6 + 1
+    assert advection_halo(2.0, -0.5, 100.0 / 512) == 7           # MacCormack backward pass: |dt|
+    assert advection_halo(0.0, 1.0, 1.0, bc_const_max=2.9) == 4   # a constant inflow boundary moves samples too
+    assert advection_halo(3.0, 1.0, 1.0) == 5                    # exact integers round up (fp32 rounding of dt*v/dx in the kernel)
+    with pytest.raises(ValueError):
+        advection_halo(float('inf'), 0.5, 1.0)
+    with pytest.raises(ValueError):
+        advection_halo(float('nan'), 0.5, 1.0)
+
+
+def _halo_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from phiflow_b200.dist import Slab, SlabPlume, HaloTooWide
+        from phiflow_b200._lib import Unsupported
+        res = (8, 6, 8 * world)
+        vbc = (('periodic', 'periodic'),) * 3
+        sbc = (('zg', 'zg'),) * 3
+        slab = Slab(res, (1.0, 1.0, 2.0), vbc, halo=2, device='cpu')
+        sim = SlabPlume(slab, sbc, 0.5, 0.2, (0.0, 0.0, 0.1), None)
+        H, nz = slab.halo, slab.nz
+        for zl in range(nz):
+            sim.s[:, H + zl] = float(slab.z0 + zl)
+            sim.v[2][:, H + zl] = 0.25
+        # only rank 1 holds the fast cell: every rank must still agree on the width (all_reduce MAX)
+        if rank == 1:
+            sim.v[2][0, H + 3, 2, 2] = -13.0                    # 13 * 0.5 / 2 = 3.25 cells -> h = 5
+        h = sim.required_halo()
+        assert h == 5, h
+        assert abs(sim.max_displacement - 3.25) < 1e-6
+        sim.ensure_halo(h)                                       # 5 > 2 allocated -> regrow to max(5, 4) = 5
+        assert sim.slab.halo == 5 and sim.regrown == 1 and sim.dom.cext[2] == nz + 10
+        H2 = sim.slab.halo
+        for zl in range(nz):                                     # owned planes survive the re-allocation
+            assert float(sim.s[0, H2 + zl, 0, 0]) == float(slab.z0 + zl)
+        assert float(sim.v[2][0, H2 + 3, 2, 2]) == (-13.0 if rank == 1 else 0.25)
+        sim.slab.exchange(sim.v + [sim.s], h)
+        gz = res[2]
+        for k in range(1, h + 1):
+            assert float(sim.s[0, H2 - k, 0, 0]) == (slab.z0 - k) % gz
+            assert float(sim.s[0, H2 + nz - 1 + k, 0, 0]) == (slab.z0 + nz - 1 + k) % gz
+        # wider than a slab: refused BEFORE anything is computed, as PHI_ERR_UNSUPPORTED
+        if rank == 0:
+            sim.v[2][0, H2, 0, 0] = 39.0                         # 9.75 cells -> h = 11 > 8 planes per rank
+        h = sim.required_halo()
+        assert h == 11
+        try:
+            sim.ensure_halo(h)
+            raise AssertionError('HaloTooWide not raised')
+        except HaloTooWide as err:
+            assert isinstance(err, Unsupported) and err.code == -2 and '11' in str(err)
+        with pytest.raises(ValueError):
+            sim.slab.exchange([sim.s], sim.slab.halo + 1)
+        q.put((rank, 'ok'))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_cfl_halo_regrow_and_refusal_gloo():
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_halo_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in results:
+        assert msg == 'ok', f"rank {rank}: {msg}"

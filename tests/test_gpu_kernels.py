@@ -362,8 +362,10 @@ def test_cg_known_answers_and_failure_modes():
 @pytest.mark.parametrize('vname', ['zero', 'open', 'periodic', 'mixed', 'periodic3', 'mixed3', 'wall_open3', 'open3'])
 def test_make_incompressible(vname, big):
     """tests/commit/physics/test_fluid.py:19-32: divergence after projection ~ 0; agreement with the oracle.
-    big: x extent a multiple of 128 so that the TMA ring kernels take their branch-free path on interior tiles/planes
-    while boundary planes with constant ghosts take the generic path (both must compose)."""
+    big: x extent a multiple of 128 -> warp-shuffle x neighbours inside the GENERIC ring kernel (2-D 128x24 tiles mix its fast
+    and boundary code paths).  The 3-D case (128, 16, 8) still runs the generic kernel on the generic consumer path: the
+    branch-free instantiations need nx % 256 == 0 and are covered, with an assertion on the selected variant, by
+    tests/test_gpu_variants.py."""
     vbc = ALL_V[vname]
     d = len(vbc)
     rng = np.random.default_rng(9)

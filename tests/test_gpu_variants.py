@@ -1,0 +1,237 @@
+"""
+Parity of the kernel INSTANTIATIONS that bench.py times: the branch-free TMA-ring variants `k_laplace_ring<3,*,GENERIC=false>`
+and `k_cg_ring<3,GENERIC=false,*>` (3-D, z register marching, several units per persistent CTA) are only selected when
+nx is a multiple of 256, ny a multiple of the tile height and no boundary is a constant (ring_kernels.cu: ring_all_fast).
+Every case asserts through phicuda_last_launch_info WHICH variant ran, so that a test cannot silently fall back to the
+generic kernel (round-1 verdict, "parity gap on the benchmarked kernel variants").
+
+Reference semantics: PhiML/phiml/backend/_linalg.py:52-90 (CG), PhiML/phiml/math/_nd.py:825-861 (laplace),
+phi/physics/fluid.py:94-162 (make_incompressible); oracle = oracle/oracle_np.py (pinned by tests/golden).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle_np as O
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from phiflow_b200 import _ops as ops
+    from phiflow_b200 import _lib
+
+EPS = float(np.finfo(np.float32).eps)
+PER3 = (('periodic', 'periodic'),) * 3
+ZG3 = (('zg', 'zg'),) * 3
+WALL3 = ((0.0, 0.0),) * 3                                   # closed box: pressure boundary ZERO_GRADIENT -> no constant ghosts
+PER_WALL3 = (('periodic', 'periodic'), (0.0, 0.0), ('periodic', 'periodic'))
+FAST_SHAPES = [(256, 16, 12), (512, 8, 8), (256, 64, 48)]
+DX = (0.5, 0.25, 2.0)
+
+
+class ring_nzc:
+    """Forces the z chunking of the ring (diagnostic knob PHICUDA_RING_NZC) so that a small grid yields more units than
+    persistent CTAs: the ring state (slot position, parity, register-marched planes) must carry over between units."""
+
+    def __init__(self, nzc):
+        self.nzc = nzc
+
+    def __enter__(self):
+        self.old = os.environ.get('PHICUDA_RING_NZC')
+        if self.nzc:
+            os.environ['PHICUDA_RING_NZC'] = str(self.nzc)
+
+    def __exit__(self, *exc):
+        if self.old is None:
+            os.environ.pop('PHICUDA_RING_NZC', None)
+        else:
+            os.environ['PHICUDA_RING_NZC'] = self.old
+
+
+def assert_fast(kernel, multi_unit=False):
+    info = ops.last_launch_info()
+    assert info['kernel'] == kernel, info
+    assert info['generic'] == 0, f"expected the branch-free variant, the launch selected the generic one: {info}"
+    if multi_unit:
+        assert info['total_units'] >= 2 * info['grid_ctas'], f"expected >= 2 units per persistent CTA: {info}"
+    return info
+
+
+@pytest.mark.parametrize('res', FAST_SHAPES)
+@pytest.mark.parametrize('bcname', ['periodic', 'zg', 'per_zg'])
+@pytest.mark.parametrize('batch', [1, 2])
+def test_laplace_fast_variant(res, bcname, batch):
+    bc = {'periodic': PER3, 'zg': ZG3, 'per_zg': (('periodic', 'periodic'), ('zg', 'zg'), ('zg', 'zg'))}[bcname]
+    rng = np.random.default_rng(31)
+    multi = res == (256, 64, 48) and batch == 2
+    with ring_nzc(12 if multi else 0):
+        dom = ops.Domain(res, DX, batch)
+        a = rng.standard_normal((batch,) + res).astype(np.float32)
+        da = dom.centered_from_numpy(a)
+        out = dom.centered_to_numpy(ops.laplace(dom, bc, da), squeeze=False)
+        assert_fast(_lib.KERNEL_LAPLACE_RING, multi)
+        out2 = dom.centered_to_numpy(ops.laplace_axpy(dom, bc, da, 0.01), squeeze=False)
+        assert_fast(_lib.KERNEL_LAPLACE_RING, multi)
+    ref = np.stack([O.laplace(a[b], DX, bc) for b in range(batch)])
+    scale = np.abs(a).max() * sum(4.0 / h ** 2 for h in DX)
+    np.testing.assert_allclose(out, ref, rtol=0, atol=4 * EPS * scale)
+    np.testing.assert_allclose(out2, a + np.float32(0.01) * ref, rtol=0, atol=4 * EPS * scale)
+
+
+@pytest.mark.parametrize('res', FAST_SHAPES)
+@pytest.mark.parametrize('vname', ['periodic', 'wall', 'per_wall'])
+def test_cg_fast_variant(res, vname):
+    """rtol 1e-3 solve (the bench's tolerance) on the benchmarked instantiation, batch 2 with different scales."""
+    vbc = {'periodic': PER3, 'wall': WALL3, 'per_wall': PER_WALL3}[vname]
+    rng = np.random.default_rng(32)
+    batch = 2
+    multi = res == (256, 64, 48)
+    rhs = rng.standard_normal((batch,) + res).astype(np.float32)
+    rhs[1] *= 5.0
+    A = O.poisson_matrix(res, DX, O.pressure_bc(vbc))
+    rtol = 1e-3
+    with ring_nzc(12 if multi else 0):
+        dom = ops.Domain(res, DX, batch, vbc=vbc)
+        prm = ops.cg_params(vbc, rtol=rtol, atol=1e-5, max_iter=1000)
+        got = dom.centered_to_numpy(ops.cg_poisson(dom, vbc, dom.centered_from_numpy(rhs), None, prm), squeeze=False)
+        assert_fast(_lib.KERNEL_CG_RING, multi)
+    info = ops.read_results(dom)
+    for b in range(batch):
+        y = rhs[b] - rhs[b].mean()
+        ref = O.cg(A, y, np.zeros(res, np.float32), rtol, 1e-5, 1000, None)
+        assert info['converged'][b] == 1 and info['diverged'][b] == 0
+        assert abs(int(info['iterations'][b]) - ref['iterations']) <= max(2, ref['iterations'] // 10), (info['iterations'][b], ref['iterations'])
+        r = y.ravel() - A.dot(got[b].ravel().astype(np.float64))
+        tol_sq = max(rtol ** 2 * float(np.sum(y.astype(np.float64) ** 2)), 1e-10)
+        assert float(np.sum(r * r)) <= 4 * tol_sq + 1e-9
+        xr = ref['x'].reshape(res)
+        xr = xr - xr.mean()
+        assert abs(got[b].mean()) < 1e-4 * max(1.0, np.abs(got[b]).max())
+        np.testing.assert_allclose(got[b], xr, rtol=0, atol=20 * rtol * np.abs(xr).max())
+
+
+@pytest.mark.parametrize('res', FAST_SHAPES)
+@pytest.mark.parametrize('method', ['CG', 'CG-adaptive'])
+def test_cg_fast_variant_truncated_iterates(res, method):
+    """Exactly k iterations for odd and even k (deferred x update, double-buffered directions) on the benchmarked variant."""
+    vbc = PER3
+    rng = np.random.default_rng(33)
+    batch = 2
+    multi = res == (256, 64, 48)
+    rhs = rng.standard_normal((batch,) + res).astype(np.float32)
+    rhs[1] *= 3.0
+    A = O.poisson_matrix(res, DX, O.pressure_bc(vbc))
+    solver = O.cg if method == 'CG' else O.cg_adaptive
+    with ring_nzc(12 if multi else 0):
+        dom = ops.Domain(res, DX, batch, vbc=vbc)
+        for k in (1, 2, 3, 4, 7):
+            prm = ops.cg_params(vbc, rtol=1e-12, atol=0.0, max_iter=k, method=method)
+            got = dom.centered_to_numpy(ops.cg_poisson(dom, vbc, dom.centered_from_numpy(rhs), None, prm), squeeze=False)
+            li = assert_fast(_lib.KERNEL_CG_RING, multi)
+            assert li['adaptive'] == (method != 'CG')
+            info = ops.read_results(dom)
+            for b in range(batch):
+                y = rhs[b] - rhs[b].mean()
+                ref = solver(A, y, np.zeros(res, np.float32), 1e-12, 0.0, k, None)
+                assert info['iterations'][b] == k == ref['iterations'] and info['converged'][b] == 0
+                xr = ref['x'].reshape(res)
+                xr = xr - xr.mean()
+                np.testing.assert_allclose(got[b], xr, rtol=0, atol=2e-5 * max(1.0, np.abs(xr).max()))
+
+
+@pytest.mark.parametrize('res', FAST_SHAPES)
+@pytest.mark.parametrize('vname', ['periodic', 'wall'])
+def test_make_incompressible_fast_variant(res, vname):
+    vbc = {'periodic': PER3, 'wall': WALL3}[vname]
+    rng = np.random.default_rng(34)
+    dx = tuple(100.0 / r for r in res)
+    multi = res == (256, 64, 48)
+    v = [(0.1 * rng.standard_normal(s)).astype(np.float32) for s in O.staggered_shapes(res, vbc)]
+    with ring_nzc(12 if multi else 0):
+        dom = ops.Domain(res, dx, 1, vbc=vbc)
+        dv = dom.faces_from_numpy(v, vbc)
+        prm = ops.cg_params(vbc, rtol=1e-5, atol=1e-5)
+        dv, p = ops.make_incompressible(dom, vbc, dv, None, prm)
+        info = ops.last_launch_info()
+    assert info['kernel'] == _lib.KERNEL_CG_RING and info['generic'] == 0, info
+    assert ops.read_results(dom)['converged'][0] == 1
+    div = dom.centered_to_numpy(ops.divergence(dom, vbc, dv))
+    vscale = max(np.abs(c).max() for c in v) * sum(2.0 / h for h in dx)
+    assert np.abs(div).max() < max(5e-5, 1e-4 * vscale)
+    v_ref, p_ref, _ = O.make_incompressible(v, vbc, res, dx, rtol=1e-5, atol=1e-5, use_matrix_offset=False)
+    got = dom.faces_to_numpy(dv, vbc)
+    for c in range(3):
+        np.testing.assert_allclose(got[c], v_ref[c], rtol=0, atol=1e-4 * max(np.abs(v[c]).max(), 1e-3))
+
+
+def _plume_parity(res, steps, expect_fast):
+    """The step bench.py times (phicuda_plume_step_f32 through ops.plume_step: periodic velocity, open smoke, inflow sphere,
+    buoyancy along z, CG rtol 1e-3 warm start) against the oracle restatement of the notebook step."""
+    vbc, sbc = PER3, ZG3
+    lower, upper = (0.0,) * 3, (100.0,) * 3
+    dx = tuple(100.0 / r for r in res)
+    inflow = O.sphere_soft_mask((50.0, 50.0, 20.0), 12.0, lower, upper, res)
+    rng = np.random.default_rng(0)
+    v = [(0.01 * rng.standard_normal(s)).astype(np.float32) for s in O.staggered_shapes(res, vbc)]
+    A = O.poisson_matrix(res, dx, O.pressure_bc(vbc))
+    v, _, _ = O.make_incompressible(v, vbc, res, dx, 1e-5, 1e-5, 1000, matrix=A, use_matrix_offset=False)
+    s = np.zeros(res, np.float32)
+    p = np.zeros(res, np.float32)
+    dom = ops.Domain(res, dx, 1, vbc=vbc)
+    dv, ds, dp = dom.faces_from_numpy(v, vbc), dom.centered_from_numpy(s), dom.centered_from_numpy(p)
+    dinflow = dom.centered_from_numpy(inflow)
+    prm = ops.cg_params(vbc, rtol=1e-3, atol=1e-5)
+    for _ in range(steps):
+        ops.plume_step(dom, vbc, sbc, dv, ds, dp, dinflow, 0.5, 0.2, (0.0, 0.0, 0.1), prm)
+        info = ops.last_launch_info()
+        assert info['kernel'] == _lib.KERNEL_CG_RING and info['generic'] == (0 if expect_fast else 1), info
+        v, s, p, oinfo = O.plume_step(v, s, p, 0.5, vbc, sbc, lower, upper, res, inflow, 0.2, (0.0, 0.0, 0.1), rtol=1e-3, atol=1e-5,
+                                      use_matrix_offset=False, matrix=A)
+        r = ops.read_results(dom)
+        assert r['converged'][0] == 1
+        assert abs(int(r['iterations'][0]) - oinfo['iterations']) <= max(3, oinfo['iterations'] // 8), (r['iterations'][0], oinfo['iterations'])
+    np.testing.assert_allclose(dom.centered_to_numpy(ds), s, rtol=0, atol=2e-4 * max(np.abs(s).max(), 1e-3))
+    got = dom.faces_to_numpy(dv, vbc)
+    vmax = max(np.abs(c).max() for c in v)
+    for c in range(3):
+        # both sides stop at |r| <= 1e-3 |r0|: velocities agree to a few times that tolerance
+        np.testing.assert_allclose(got[c], v[c], rtol=0, atol=2e-2 * vmax)
+    div = dom.centered_to_numpy(ops.divergence(dom, vbc, dv))
+    ref_div = O.divergence_staggered(v, dx, O.component_bcs(vbc, 3))
+    assert np.abs(div).max() <= 3 * max(np.abs(ref_div).max(), 1e-6)
+
+
+def test_plume_step_bench_sequence_fast_variant():
+    _plume_parity((256, 32, 24), 5, expect_fast=True)
+
+
+def test_plume_step_bench_sequence_96():
+    """96^3, the grid the CPU baseline is sampled at."""
+    _plume_parity((96, 96, 96), 3, expect_fast=False)
+
+
+def test_max_abs_velocity():
+    rng = np.random.default_rng(35)
+    for vbc, res in [(PER3, (40, 12, 9)), (((0.0, 0.0), ('zg', 'zg'), (0.0, 'zg')), (21, 14, 9)),
+                     ((('zg', 'zg'), (0.0, 0.0)), (37, 22))]:
+        d = len(res)
+        dom = ops.Domain(res, (1.0,) * d, 2, vbc=vbc)
+        v = [rng.standard_normal((2,) + s).astype(np.float32) for s in O.staggered_shapes(res, vbc)]
+        dv = dom.faces_from_numpy(v, vbc)
+        for t in dv:                                  # unused slots of the allocation must not count
+            pass
+        got = ops.max_abs_velocity(dom, vbc, dv).cpu().numpy()
+        for c in range(d):
+            assert got[c] == np.abs(v[c]).max()
+    # slots outside the stored range are ignored even when they hold garbage
+    vbc, res = WALL3, (12, 10, 8)
+    dom = ops.Domain(res, (1.0,) * 3, 1, vbc=vbc)
+    v = [rng.standard_normal(s).astype(np.float32) for s in O.staggered_shapes(res, vbc)]
+    dv = dom.faces_from_numpy(v, vbc)
+    dv[0][:, :, :, 0] = 1e9                            # x face 0 of a closed box is not stored
+    dv[2][:, 0] = 1e9
+    got = ops.max_abs_velocity(dom, vbc, dv).cpu().numpy()
+    for c in range(3):
+        assert got[c] == np.abs(v[c]).max()

@@ -49,9 +49,11 @@ def run_case(name, vbc, sbc, res, steps, rtol):
     iters = []
     for _ in range(steps):
         sim.step()
-        iters.append(int(slab.results()['iterations'][0]))
+        iters.append(int(sim.slab.results()['iterations'][0]))
         if rank == 0:
-            print(f"[{name}] dist solve result: {slab.results()}", flush=True)
+            print(f"[{name}] dist solve result: {sim.slab.results()}", flush=True)
+    slab = sim.slab
+    d, H = slab.dom, slab.halo
     s_all = gather_centered(slab, sim.s)
     p_all = gather_centered(slab, sim.p)
     div = ops.divergence(d, slab.vbc, sim.v)          # needs v halo of the upper neighbour
@@ -100,6 +102,69 @@ def run_case(name, vbc, sbc, res, steps, rtol):
     return bool(flag.item())
 
 
+def run_oracle_case(name, disp_cells, steps, rtol=1e-5, start_halo=3):
+    """CFL-derived advection halo against the ORACLE (not only against the single-GPU kernels): a periodic plume whose
+    z velocity moves samples `disp_cells` cells per step - more than the 4 planes round 1 hard-coded, and more than the
+    `start_halo` planes allocated at the start, so the state is re-allocated with a wider halo on the way
+    (reference: the unbounded back-trace of phi/physics/advect.py:20-24, 156-179)."""
+    from oracle import oracle_np as O
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    res = (64, 48, 16 * world)
+    nx, ny, nz = res
+    dx = tuple(100.0 / r for r in res)
+    vbc, sbc = (('periodic', 'periodic'),) * 3, (('zg', 'zg'),) * 3
+    dt = 0.5
+    xs, ys, zs = np.meshgrid((np.arange(nx) + .5) / nx, (np.arange(ny) + .5) / ny, (np.arange(nz) + .5) / nz, indexing='ij')
+    w0 = disp_cells * dx[2] / dt
+    rng = np.random.default_rng(11)
+    v = [(0.3 * w0 * np.sin(2 * np.pi * ys) * np.cos(2 * np.pi * zs) + 0.02 * w0 * rng.standard_normal(res)).astype(np.float32),
+         (0.2 * w0 * np.cos(2 * np.pi * xs) * np.sin(4 * np.pi * zs) + 0.02 * w0 * rng.standard_normal(res)).astype(np.float32),
+         (w0 * (0.8 + 0.15 * np.sin(2 * np.pi * xs) * np.cos(2 * np.pi * ys)) + 0.02 * w0 * rng.standard_normal(res)).astype(np.float32)]
+    inflow = O.sphere_soft_mask((50.0, 50.0, 30.0), 15.0, (0.0,) * 3, (100.0,) * 3, res)
+    s0 = (0.5 + 0.5 * np.sin(2 * np.pi * xs) * np.sin(2 * np.pi * ys) * np.cos(2 * np.pi * zs)).astype(np.float32)
+    prm = ops.cg_params(vbc, rtol=rtol, atol=1e-7, max_iter=3000)
+    slab = Slab(res, dx, vbc, halo=start_halo, device=dev)
+    sim = SlabPlume(slab, sbc, dt, 0.2, (0.0, 0.0, 0.1), prm)
+    H, nzl, z0 = slab.halo, slab.nz, slab.z0
+    to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a[:, :, z0:z0 + nzl].transpose(2, 1, 0))).to(dev)
+    for c in range(3):
+        sim.v[c][0, H:H + nzl, :ny, :nx] = to_dev(v[c])
+    sim.s[0, H:H + nzl, :ny, :nx] = to_dev(s0)
+    sim.inflow[0, H:H + nzl, :ny, :nx] = to_dev(inflow)
+    sim.project()
+    for _ in range(steps):
+        sim.step()
+    slab = sim.slab
+    own = lambda t: t[:, slab.halo:slab.halo + nzl, :ny, :nx].contiguous()
+    def gather(t):
+        parts = [torch.empty_like(own(t)) for _ in range(world)]
+        dist.all_gather(parts, own(t))
+        return torch.cat(parts, dim=1)[0].permute(2, 1, 0).cpu().numpy()
+    s_all = gather(sim.s)
+    v_all = [gather(sim.v[c]) for c in range(3)]
+    ok = True
+    if rank == 0:
+        A = O.poisson_matrix(res, dx, O.pressure_bc(vbc))
+        vr, pr, _ = O.make_incompressible(v, vbc, res, dx, rtol, 1e-7, 3000, matrix=A, use_matrix_offset=False)
+        sr = s0
+        for _ in range(steps):
+            vr, sr, pr, info = O.plume_step(vr, sr, pr, dt, vbc, sbc, (0.0,) * 3, (100.0,) * 3, res, inflow, 0.2, (0.0, 0.0, 0.1),
+                                            rtol=rtol, atol=1e-7, max_iter=3000, use_matrix_offset=False, matrix=A)
+        vmax = max(float(np.abs(c).max()) for c in vr)
+        ds = float(np.abs(s_all - sr).max())
+        dv = [float(np.abs(v_all[c] - vr[c]).max()) for c in range(3)]
+        need = int(np.ceil(sim.max_displacement)) + 1
+        print(f"[{name}] world={world} vs ORACLE: max|s diff|={ds:.3e} (max {float(np.abs(sr).max()):.3e}) max|v diff|={dv} (vmax {vmax:.3e}) "
+              f"displacement={sim.max_displacement:.2f} cells, halo used={sim.halo_used}, allocated={slab.halo}, regrown={sim.regrown}", flush=True)
+        ok = ds <= 5e-4 * max(float(np.abs(sr).max()), 1e-3) and all(d <= 2e-3 * vmax for d in dv)
+        ok = ok and sim.max_displacement > 4.0 and sim.halo_used >= need and sim.regrown >= 1
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    slab.close()
+    return bool(flag.item())
+
+
 def main():
     dist.init_process_group('nccl')
     torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
@@ -110,6 +175,7 @@ def main():
     ok = True
     ok &= run_case('periodic', per, zg, (64, 48, 16 * world), 3, 1e-4)
     ok &= run_case('mixed-z-wall-open', mixed, zg, (128, 24, 8 * world), 2, 1e-4)
+    ok &= run_oracle_case('cfl-halo-vs-oracle', 6.4, 3)
     if dist.get_rank() == 0:
         print('DIST_CHECK', 'PASS' if ok else 'FAIL', flush=True)
     dist.destroy_process_group()
