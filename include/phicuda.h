@@ -210,15 +210,22 @@ int phicuda_make_incompressible_masked_f32(const PhiGrid* g, const PhiVBC* vbc, 
                                            const float* accessible, const PhiCgParams* prm, PhiCgResult* result,
                                            void* workspace, size_t workspace_bytes, void* stream);
 
-/* ---- incompressible_step: the fused notebook step -----------------------------------------------
+/* ---- incompressible_step: the notebook step as ONE call -------------------------------------------
  * s' = advect(s, v, dt) + inflow_rate * inflow ; v* = semi_lagrangian(v, v, dt) + dt * buoyancy(s') ;
  * v', p' = make_incompressible(v*, Solve('CG', x0 = p)).   mac_cormack != 0 selects advect.mac_cormack for s.
+ * Five kernel launches + one device copy: inflow and buoyancy are epilogues of the two advection kernels (all staggered
+ * components advected in one launch), the projected velocity is written straight into v.
  * All state is updated in place; scratch = 2 centred + dim staggered arrays (phicuda_plume_scratch_bytes). */
 typedef struct PhiPlumeParams {
     float   dt;
     float   inflow_rate;
     float   buoyancy[3];
     int32_t mac_cormack;
+    int32_t static_scalar;   /* 1: `s` is a stationary source (body force / forcing field, e.g. the Kolmogorov sin(4y) forcing): it is
+                                not advected and gets no inflow; the step is v* = semi_lagrangian(v, v, dt) + dt * resample(s * b, to=v),
+                                then the projection */
+    void*   cg_start_event;  /* optional cudaEvent_t handles recorded on `stream` right before / after the pressure solve, */
+    void*   cg_stop_event;   /* so a caller can time the CG kernel inside the single fused call (bench.py roofline); or NULL */
 } PhiPlumeParams;
 size_t phicuda_plume_scratch_bytes(const PhiGrid* g);
 int phicuda_plume_step_f32(const PhiGrid* g, const PhiVBC* vbc, const PhiBC* sbc, float* const v[3], float* s, float* p,

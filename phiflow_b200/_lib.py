@@ -47,7 +47,8 @@ KERNEL_NONE, KERNEL_LAPLACE_RING, KERNEL_LAPLACE_MARCH, KERNEL_CG_RING, KERNEL_C
 
 
 class PhiPlumeParams(C.Structure):
-    _fields_ = [('dt', C.c_float), ('inflow_rate', C.c_float), ('buoyancy', C.c_float * 3), ('mac_cormack', C.c_int32)]
+    _fields_ = [('dt', C.c_float), ('inflow_rate', C.c_float), ('buoyancy', C.c_float * 3), ('mac_cormack', C.c_int32), ('static_scalar', C.c_int32),
+                ('cg_start_event', C.c_void_p), ('cg_stop_event', C.c_void_p)]
 
 
 F3 = C.c_void_p * 3          # float* const v[3]

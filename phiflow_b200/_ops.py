@@ -340,16 +340,71 @@ def make_incompressible(dom: Domain, vbc, v, p=None, prm: PhiCgParams = None, ac
     return v, p
 
 
-def plume_step(dom: Domain, vbc, sbc, v, s, p, inflow, dt, inflow_rate, buoyancy, prm: PhiCgParams, mac_cormack=False):
-    """incompressible_step: the fused notebook step (examples/grids/Smoke_Plume.ipynb:58-68); state updated in place."""
+def plume_step(dom: Domain, vbc, sbc, v, s, p, inflow, dt, inflow_rate, buoyancy, prm: PhiCgParams, mac_cormack=False, cg_events=None,
+               static_scalar=False):
+    """incompressible_step: the notebook step (examples/grids/Smoke_Plume.ipynb:58-68) as one C-ABI call; state updated in place.
+    cg_events: optional pair of torch.cuda.Event(enable_timing=True) that the library records around the pressure solve.
+    static_scalar: `s` is a stationary forcing field (v* = advect(v) + dt * resample(s * buoyancy, to=v)), not advected smoke."""
     require_cuda()
     assert dom.halo == 0, "plume_step is the single-GPU fused call; z-slab runs sequence the step in phiflow_b200.dist"
     ws, res = dom.workspace()
     sp = PhiPlumeParams()
-    sp.dt, sp.inflow_rate, sp.mac_cormack = dt, inflow_rate, int(mac_cormack)
+    sp.dt, sp.inflow_rate, sp.mac_cormack, sp.static_scalar = dt, inflow_rate, int(mac_cormack), int(static_scalar)
     for i in range(3):
         sp.buoyancy[i] = float(buoyancy[i]) if i < len(buoyancy) else 0.0
+    if cg_events is not None:
+        for ev in cg_events:
+            if not ev.cuda_event:                   # torch creates the cudaEvent_t lazily at the first record
+                ev.record()
+        sp.cg_start_event, sp.cg_stop_event = cg_events[0].cuda_event, cg_events[1].cuda_event
     _lib.check(_lib.load().phicuda_plume_step_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), C.byref(make_bc(sbc)), _f3(v),
                                                   _ptr(s), _ptr(p), _ptr(inflow), C.byref(sp), C.byref(prm), _ptr(res),
                                                   _ptr(dom.scratch()), _ptr(ws), C.c_size_t(ws.numel()), _stream()))
     return v, s, p
+
+
+class HostPlume:
+    """The reference-facing form of the step: the state (v components, s, p) lives in HOST arrays in the reference's
+    (x, y[, z]) order (`Field.numpy()` order, phi/field/_field.py:170-172); every call uploads it from pinned memory,
+    transposes to the device layout, runs phicuda_plume_step_f32, transposes back and downloads the
+    new state.  This is what bench.py times as `e2e`."""
+
+    def __init__(self, dom: Domain, vbc, sbc):
+        require_cuda()
+        self.dom, self.vbc, self.sbc = dom, vbc, sbc
+        shapes, self.offsets = dom.face_shapes(vbc)
+        pin = lambda shape: torch.zeros(shape, dtype=torch.float32).pin_memory()
+        self.v = [pin(shapes[c]) for c in range(dom.dim)]
+        self.s, self.p = pin(dom.res), pin(dom.res)
+        self.dv, self.ds, self.dp = dom.alloc_faces(), dom.alloc_centered(), dom.alloc_centered()
+        self.bytes_per_direction = 4 * (sum(t.numel() for t in self.v) + self.s.numel() + self.p.numel())
+        self._perm = tuple(range(dom.dim - 1, -1, -1))
+
+    def _view(self, t, shape, axis=None, offset=0):
+        idx = [0]
+        for ax in range(self.dom.dim - 1, -1, -1):
+            start = offset if ax == axis else 0
+            idx.append(slice(start, start + shape[ax]))
+        return t[tuple(idx)]
+
+    def load(self, v_dev, s_dev, p_dev):
+        """Seeds the host state from device arrays (set-up, untimed)."""
+        shapes, offs = self.dom.face_shapes(self.vbc)
+        for c in range(self.dom.dim):
+            self.v[c].copy_(self._view(v_dev[c], shapes[c], c, offs[c]).permute(*self._perm))
+        self.s.copy_(self._view(s_dev, self.dom.res).permute(*self._perm))
+        self.p.copy_(self._view(p_dev, self.dom.res).permute(*self._perm))
+        torch.cuda.synchronize()
+
+    def step(self, inflow_dev, dt, inflow_rate, buoyancy, prm, **kw):
+        dom, dev = self.dom, self.dom.device
+        shapes, offs = dom.face_shapes(self.vbc)
+        for c in range(dom.dim):
+            self._view(self.dv[c], shapes[c], c, offs[c]).copy_(self.v[c].to(dev, non_blocking=True).permute(*self._perm))
+        self._view(self.ds, dom.res).copy_(self.s.to(dev, non_blocking=True).permute(*self._perm))
+        self._view(self.dp, dom.res).copy_(self.p.to(dev, non_blocking=True).permute(*self._perm))
+        plume_step(dom, self.vbc, self.sbc, self.dv, self.ds, self.dp, inflow_dev, dt, inflow_rate, buoyancy, prm, **kw)
+        for c in range(dom.dim):
+            self.v[c].copy_(self._view(self.dv[c], shapes[c], c, offs[c]).permute(*self._perm), non_blocking=True)
+        self.s.copy_(self._view(self.ds, dom.res).permute(*self._perm), non_blocking=True)
+        self.p.copy_(self._view(self.dp, dom.res).permute(*self._perm), non_blocking=True)

@@ -190,9 +190,10 @@ int phi_launch_advect(const DGrid& g, const DVec& vel, const DField& ff, int tar
 int phi_launch_mac_cormack(const DGrid& g, const DVec& vel, const DField& ff, const float* src, float* dst, float* tmp,
                            float dt, float strength, cudaStream_t s)
 {
-    int err = phi_launch_advect(g, vel, ff, -1, src, tmp, dt, s);
+    const bool vec = !phi_scalar_kernels();
+    int err = vec ? phi_launch_advect_centered_vec(g, vel, ff, src, tmp, dt, nullptr, 0.f, s) : phi_launch_advect(g, vel, ff, -1, src, tmp, dt, s);
     if (err) return err;
-    err = phi_launch_advect(g, vel, ff, -1, tmp, dst, -dt, s);
+    err = vec ? phi_launch_advect_centered_vec(g, vel, ff, tmp, dst, -dt, nullptr, 0.f, s) : phi_launch_advect(g, vel, ff, -1, tmp, dst, -dt, s);
     if (err) return err;
     const float hs = strength * 0.5f;
     if (g.dim == 3) k_mac_cormack_combine<3><<<scalar_grid(g), 128, 0, s>>>(g, vel, ff, src, tmp, dst, dt, hs);

@@ -25,6 +25,12 @@ bool phi_ring_enabled()
     return !(v && v[0] == '1');
 }
 
+bool phi_scalar_kernels()
+{
+    const char* v = getenv("PHICUDA_SCALAR_KERNELS");    // diagnostics / A-B parity: the round-1 one-thread-per-sample kernels
+    return v && v[0] == '1';
+}
+
 static int cuda_fail(int err, const char* what)
 {
     if (err > 0) phi_set_error("%s: %s", what, cudaGetErrorString((cudaError_t)err));
@@ -218,6 +224,7 @@ int phicuda_divergence_f32(const PhiGrid* g, const PhiVBC* vbc, const float* con
     DGrid dg; DVec dv; DField cf; PhiBC none; memset(&none, 0, sizeof(none));
     CHECK(phi_make_dgrid(g, &dg)); CHECK(make_vec(g, vbc, v, &dv)); CHECK(phi_make_centered(g, &none, &cf));
     if (!div) { phi_set_error("divergence: div is NULL"); return PHI_ERR_INVALID; }
+    if (!phi_scalar_kernels()) return cuda_fail(phi_launch_divergence_vec(dg, dv, cf, div, (cudaStream_t)stream), "divergence");
     return cuda_fail(phi_launch_divergence(dg, dv, cf, div, nullptr, (cudaStream_t)stream), "divergence");
 }
 
@@ -228,6 +235,7 @@ int phicuda_grad_sub_f32(const PhiGrid* g, const PhiVBC* vbc, float* const v[3],
     CHECK(phi_pressure_bc(vbc, g->dim, &pbc)); CHECK(phi_make_centered(g, &pbc, &pf));
     if (!p) { phi_set_error("grad_sub: p is NULL"); return PHI_ERR_INVALID; }
     for (int c = 0; c < 3; ++c) out.p[c] = c < g->dim ? v[c] : nullptr;
+    if (!phi_scalar_kernels()) return cuda_fail(phi_launch_grad_sub_vec(dg, dv, out, pf, p, (cudaStream_t)stream), "grad_sub");
     return cuda_fail(phi_launch_grad_sub(dg, dv, out, pf, p, nullptr, nullptr, (cudaStream_t)stream), "grad_sub");
 }
 
@@ -237,6 +245,7 @@ int phicuda_advect_centered_f32(const PhiGrid* g, const PhiVBC* vbc, const float
     DGrid dg; DVec dv; DField ff;
     CHECK(phi_make_dgrid(g, &dg)); CHECK(make_vec(g, vbc, vel, &dv)); CHECK(phi_make_centered(g, fbc, &ff));
     if (!src || !dst || src == dst) { phi_set_error("advect: src and dst must be distinct non-NULL arrays"); return PHI_ERR_INVALID; }
+    if (!phi_scalar_kernels()) return cuda_fail(phi_launch_advect_centered_vec(dg, dv, ff, src, dst, dt, nullptr, 0.f, (cudaStream_t)stream), "advect_centered");
     return cuda_fail(phi_launch_advect(dg, dv, ff, -1, src, dst, dt, (cudaStream_t)stream), "advect_centered");
 }
 
@@ -248,6 +257,10 @@ int phicuda_advect_staggered_f32(const PhiGrid* g, const PhiVBC* vbc, const floa
     for (int c = 0; c < g->dim; ++c) {
         if (!dst[c]) { phi_set_error("advect: dst[%d] is NULL", c); return PHI_ERR_INVALID; }
         for (int k = 0; k < g->dim; ++k) if (dst[c] == src[k] || dst[c] == vel[k]) { phi_set_error("advect: dst must not alias src or vel"); return PHI_ERR_INVALID; }
+    }
+    if (!phi_scalar_kernels()) {      // all components in one launch: the velocity lines are loaded once and shared
+        DVecOut out; for (int c = 0; c < 3; ++c) out.p[c] = c < g->dim ? dst[c] : nullptr;
+        return cuda_fail(phi_launch_advect_staggered_vec(dg, dv, df, out, dt, nullptr, nullptr, nullptr, (cudaStream_t)stream), "advect_staggered");
     }
     for (int c = 0; c < g->dim; ++c)
         CHECK(cuda_fail(phi_launch_advect(dg, dv, df.f[c], c, src[c], dst[c], dt, (cudaStream_t)stream), "advect_staggered"));
@@ -360,13 +373,32 @@ int phicuda_cg_poisson_f32(const PhiGrid* g, const PhiVBC* vbc, const float* rhs
     return phi_launch_cg(l, (cudaStream_t)stream);
 }
 
+// div -> CG -> v = vin - grad p.  vin/vout may be the same arrays (make_incompressible) or scratch -> state (fused step).
+static int project(const PhiGrid* g, const PhiVBC* vbc, const float* const vin[3], float* const vout[3], float* p, float* div,
+                   const PhiCgParams* prm, PhiCgResult* result, void* workspace, size_t workspace_bytes, void* ev0, void* ev1, void* stream)
+{
+    DGrid dg; DVec dv; DVecOut out; DField cf, pf; PhiBC none, pbc; memset(&none, 0, sizeof(none));
+    CHECK(phi_make_dgrid(g, &dg)); CHECK(make_vec(g, vbc, vin, &dv)); CHECK(phi_make_centered(g, &none, &cf));
+    CHECK(phi_pressure_bc(vbc, g->dim, &pbc)); CHECK(phi_make_centered(g, &pbc, &pf));
+    if (!p || !div || !vout) { phi_set_error("make_incompressible: NULL argument"); return PHI_ERR_INVALID; }
+    for (int c = 0; c < 3; ++c) {
+        out.p[c] = c < g->dim ? vout[c] : nullptr;
+        if (c < g->dim && !vout[c]) { phi_set_error("make_incompressible: output component %d is NULL", c); return PHI_ERR_INVALID; }
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool scalar = phi_scalar_kernels();
+    CHECK(cuda_fail(scalar ? phi_launch_divergence(dg, dv, cf, div, nullptr, st) : phi_launch_divergence_vec(dg, dv, cf, div, st), "divergence"));
+    if (ev0) CHECK(cuda_fail(cudaEventRecord((cudaEvent_t)ev0, st), "cudaEventRecord"));
+    CHECK(phicuda_cg_poisson_f32(g, vbc, div, p, prm, result, workspace, workspace_bytes, stream));
+    if (ev1) CHECK(cuda_fail(cudaEventRecord((cudaEvent_t)ev1, st), "cudaEventRecord"));
+    return cuda_fail(scalar ? phi_launch_grad_sub(dg, dv, out, pf, p, nullptr, nullptr, st) : phi_launch_grad_sub_vec(dg, dv, out, pf, p, st), "grad_sub");
+}
+
 int phicuda_make_incompressible_f32(const PhiGrid* g, const PhiVBC* vbc, float* const v[3], float* p, float* div,
                                     const PhiCgParams* prm, PhiCgResult* result, void* workspace,
                                     size_t workspace_bytes, void* stream)
 {
-    CHECK(phicuda_divergence_f32(g, vbc, v, div, stream));
-    CHECK(phicuda_cg_poisson_f32(g, vbc, div, p, prm, result, workspace, workspace_bytes, stream));
-    return phicuda_grad_sub_f32(g, vbc, v, p, stream);
+    return project(g, vbc, v, v, p, div, prm, result, workspace, workspace_bytes, nullptr, nullptr, stream);
 }
 
 static size_t centred_elems(const PhiGrid* g) { return (size_t)g->cext[0] * g->cext[1] * (g->dim == 3 ? g->cext[2] : 1) * g->batch; }
@@ -381,30 +413,50 @@ int phicuda_plume_step_f32(const PhiGrid* g, const PhiVBC* vbc, const PhiBC* sbc
                            const float* inflow, const PhiPlumeParams* sp, const PhiCgParams* prm, PhiCgResult* result,
                            float* scratch, void* workspace, size_t workspace_bytes, void* stream)
 {
-    DGrid dg;
+    // Launch sequence (5 kernels + 1 device copy; round 1: 9 kernels + 4 copies):
+    //   1. s_new = interp(s, x - dt v) + rate * inflow                      advection with the inflow as epilogue
+    //   2. v*    = interp(v, faces - dt v) + dt * buoyancy(s_new)           all components in one launch, buoyancy as epilogue
+    //   3. s     <- s_new                                                    (the only copy: s cannot be advected in place)
+    //   4. div   = divergence(v*)     5. p = CG(div, x0 = p)                 6. v = v* - grad p   (written into the caller's v)
+    DGrid dg; DVec dv; DField sf;
     CHECK(phi_make_dgrid(g, &dg));
-    if (!sp || !scratch || !s || !p) { phi_set_error("plume_step: NULL argument"); return PHI_ERR_INVALID; }
+    if (!sp || !scratch || !s || !p || !v) { phi_set_error("plume_step: NULL argument"); return PHI_ERR_INVALID; }
+    CHECK(make_vec(g, vbc, v, &dv)); CHECK(phi_make_centered(g, sbc, &sf));
     const size_t carr = centred_elems(g), farr = face_elems(g);
     float* s_new = scratch;                 // advected smoke
     float* tmp = scratch + carr;            // MacCormack scratch, later the divergence
     float* vn[3] = {nullptr, nullptr, nullptr};
-    for (int c = 0; c < g->dim; ++c) vn[c] = scratch + 2 * carr + c * farr;
-    // s' = advect(s, v, dt) + inflow_rate * inflow
-    if (sp->mac_cormack) CHECK(phicuda_mac_cormack_centered_f32(g, vbc, v, sbc, s, s_new, tmp, sp->dt, 1.0f, stream));
-    else                 CHECK(phicuda_advect_centered_f32(g, vbc, v, sbc, s, s_new, sp->dt, stream));
-    if (inflow && sp->inflow_rate != 0.f) CHECK(phicuda_axpy_centered_f32(g, sp->inflow_rate, inflow, s_new, stream));
-    // v* = semi_lagrangian(v, v, dt) + dt * buoyancy(s')
-    CHECK(phicuda_advect_staggered_f32(g, vbc, v, vbc, v, vn, sp->dt, stream));
-    CHECK(phicuda_add_buoyancy_f32(g, vbc, sbc, s_new, sp->buoyancy, sp->dt, vn, stream));
-    // state update (device-to-device copies keep the caller's pointers valid)
+    DVecOut out;
+    for (int c = 0; c < 3; ++c) { vn[c] = c < g->dim ? scratch + 2 * carr + c * farr : nullptr; out.p[c] = vn[c]; }
     cudaStream_t st = (cudaStream_t)stream;
+    const bool has_inflow = inflow && sp->inflow_rate != 0.f;
+    if (sp->static_scalar) {                // forced step: s is a stationary source field
+        if (phi_scalar_kernels()) {
+            CHECK(phicuda_advect_staggered_f32(g, vbc, v, vbc, v, vn, sp->dt, stream));
+            CHECK(phicuda_add_buoyancy_f32(g, vbc, sbc, s, sp->buoyancy, sp->dt, vn, stream));
+        } else {
+            CHECK(cuda_fail(phi_launch_advect_staggered_vec(dg, dv, dv, out, sp->dt, &sf, s, sp->buoyancy, st), "advect_staggered"));
+        }
+        return project(g, vbc, vn, v, p, tmp, prm, result, workspace, workspace_bytes, sp->cg_start_event, sp->cg_stop_event, stream);
+    }
+    if (phi_scalar_kernels()) {             // round-1 sequence, kept for A/B comparisons
+        if (sp->mac_cormack) CHECK(phicuda_mac_cormack_centered_f32(g, vbc, v, sbc, s, s_new, tmp, sp->dt, 1.0f, stream));
+        else                 CHECK(phicuda_advect_centered_f32(g, vbc, v, sbc, s, s_new, sp->dt, stream));
+        if (has_inflow) CHECK(phicuda_axpy_centered_f32(g, sp->inflow_rate, inflow, s_new, stream));
+        CHECK(phicuda_advect_staggered_f32(g, vbc, v, vbc, v, vn, sp->dt, stream));
+        CHECK(phicuda_add_buoyancy_f32(g, vbc, sbc, s_new, sp->buoyancy, sp->dt, vn, stream));
+    } else {
+        if (sp->mac_cormack) {
+            CHECK(cuda_fail(phi_launch_mac_cormack(dg, dv, sf, s, s_new, tmp, sp->dt, 1.0f, st), "mac_cormack"));
+            if (has_inflow) CHECK(phicuda_axpy_centered_f32(g, sp->inflow_rate, inflow, s_new, stream));
+        } else {
+            CHECK(cuda_fail(phi_launch_advect_centered_vec(dg, dv, sf, s, s_new, sp->dt, has_inflow ? inflow : nullptr, sp->inflow_rate, st), "advect_centered"));
+        }
+        CHECK(cuda_fail(phi_launch_advect_staggered_vec(dg, dv, dv, out, sp->dt, &sf, s_new, sp->buoyancy, st), "advect_staggered"));
+    }
     cudaError_t e = cudaMemcpyAsync(s, s_new, carr * sizeof(float), cudaMemcpyDeviceToDevice, st);
     if (e) return cuda_fail(e, "plume_step copy s");
-    for (int c = 0; c < g->dim; ++c) {
-        e = cudaMemcpyAsync(v[c], vn[c], farr * sizeof(float), cudaMemcpyDeviceToDevice, st);
-        if (e) return cuda_fail(e, "plume_step copy v");
-    }
-    return phicuda_make_incompressible_f32(g, vbc, v, p, tmp, prm, result, workspace, workspace_bytes, stream);
+    return project(g, vbc, vn, v, p, tmp, prm, result, workspace, workspace_bytes, sp->cg_start_event, sp->cg_stop_event, stream);
 }
 
 }  // extern "C"

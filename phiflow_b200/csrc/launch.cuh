@@ -18,6 +18,15 @@ int phi_launch_advect(const DGrid& g, const DVec& vel, const DField& ff, int tar
 int phi_launch_mac_cormack(const DGrid& g, const DVec& vel, const DField& ff, const float* src, float* dst, float* tmp,
                            float dt, float strength, cudaStream_t s);
 
+// vectorised / fused variants (fused_kernels.cu); no obstacle masks
+int phi_launch_divergence_vec(const DGrid& g, const DVec& v, const DField& cf, float* div, cudaStream_t s);
+int phi_launch_grad_sub_vec(const DGrid& g, const DVec& vin, const DVecOut& vout, const DField& pf, const float* p, cudaStream_t s);
+int phi_launch_advect_centered_vec(const DGrid& g, const DVec& vel, const DField& ff, const float* src, float* dst, float dt,
+                                   const float* add, float add_scale, cudaStream_t s);
+int phi_launch_advect_staggered_vec(const DGrid& g, const DVec& vel, const DVec& fld, const DVecOut& dst, float dt,
+                                    const DField* sf, const float* sarr, const float bu[3], cudaStream_t s);
+bool phi_scalar_kernels();      // PHICUDA_SCALAR_KERNELS=1: diagnostics, forces the one-thread-per-sample kernels of round 1
+
 struct CgLaunch {
     DGrid g; DField pf;
     const float* rhs; float* x;
