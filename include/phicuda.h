@@ -147,6 +147,11 @@ int phicuda_advect_centered_f32(const PhiGrid* g, const PhiVBC* vbc, const float
                                 const PhiBC* fbc, const float* src, float* dst, float dt, void* stream);
 int phicuda_advect_staggered_f32(const PhiGrid* g, const PhiVBC* vbc, const float* const vel[3],
                                  const PhiVBC* fbc, const float* const src[3], float* const dst[3], float dt, void* stream);
+/* A11 alone: math.grid_sample (PhiML/phiml/math/_ops.py:936-1015) = Backend.grid_sample of the reference-side plugin
+ * (PhiML/phiml/backend/_backend.py:1578-1593).  out[b][i] = n-linear interpolation of the centred array grid[b] at
+ * coords[b][i][0..dim) (index space: 0 = first cell centre, x first), neighbours outside follow `bc`. */
+int phicuda_grid_sample_f32(const PhiGrid* g, const PhiBC* bc, const float* grid, const float* coords, int64_t npoints,
+                            float* out, void* stream);
 /* N1  advect.mac_cormack for a centred field (phi/physics/advect.py:182-215); tmp = one scratch array. */
 int phicuda_mac_cormack_centered_f32(const PhiGrid* g, const PhiVBC* vbc, const float* const vel[3],
                                      const PhiBC* fbc, const float* src, float* dst, float* tmp,

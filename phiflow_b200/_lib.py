@@ -67,6 +67,7 @@ PROTOTYPES = {
     'phicuda_grad_sub_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), F3, C.c_void_p, C.c_void_p]),
     'phicuda_advect_centered_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), F3, _P(PhiBC), C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
     'phicuda_advect_staggered_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), F3, _P(PhiVBC), F3, F3, C.c_float, C.c_void_p]),
+    'phicuda_grid_sample_f32': (C.c_int, [_P(PhiGrid), _P(PhiBC), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     'phicuda_mac_cormack_centered_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), F3, _P(PhiBC), C.c_void_p, C.c_void_p, C.c_void_p,
                                                    C.c_float, C.c_float, C.c_void_p]),
     'phicuda_axpy_centered_f32': (C.c_int, [_P(PhiGrid), C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),

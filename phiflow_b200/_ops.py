@@ -239,6 +239,18 @@ def advect_staggered(dom: Domain, vbc, vel, fbc, src, dt: float, out=None):
     return out
 
 
+def grid_sample(dom: Domain, bc, grid: torch.Tensor, coords: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+    """math.grid_sample (PhiML/phiml/math/_ops.py:936-1015): grid = centred array in device layout, coords = float32 tensor
+    (batch, npoints, dim) of index-space positions (x first, 0 = first cell centre).  Returns (batch, npoints)."""
+    require_cuda()
+    assert coords.dtype == torch.float32 and coords.is_contiguous() and coords.shape[0] == dom.batch and coords.shape[-1] == dom.dim
+    npoints = coords.shape[1]
+    out = torch.empty((dom.batch, npoints), dtype=torch.float32, device=dom.device) if out is None else out
+    _lib.check(_lib.load().phicuda_grid_sample_f32(C.byref(dom.grid), C.byref(make_bc(bc)), _ptr(grid, dom.coff), _ptr(coords),
+                                                   C.c_int64(npoints), _ptr(out), _stream()))
+    return out
+
+
 def mac_cormack_centered(dom: Domain, vbc, vel, fbc, src, dt: float, correction_strength=1.0, out=None):
     """advect.mac_cormack of a centred field (phi/physics/advect.py:182-215)."""
     require_cuda()

@@ -69,7 +69,7 @@ __device__ __forceinline__ Lookup phi_lookup(const DGrid& g, const DVec& vel, in
     for (int a = 0; a < 3; ++a) {
         if (a >= DIM) { L.i[a] = 0; L.t[a] = 0.f; continue; }
         const float v = phi_velocity_at<DIM>(g, vel, a, target, b, x, y, z);
-        const float delta = __fdiv_rn(-dt * v, g.dx[a]);
+        const float delta = phi_div(-dt * v, g.dx[a], g.inv_dx[a]);
         const float fl = floorf(delta);
         L.i[a] = idx[a] + (int)fl;
         L.t[a] = delta - fl;
@@ -190,7 +190,7 @@ int phi_launch_advect(const DGrid& g, const DVec& vel, const DField& ff, int tar
 int phi_launch_mac_cormack(const DGrid& g, const DVec& vel, const DField& ff, const float* src, float* dst, float* tmp,
                            float dt, float strength, cudaStream_t s)
 {
-    const bool vec = !phi_scalar_kernels();
+    const bool vec = !phi_scalar_kernels() && (long long)g.fext[0] * g.fext[1] * g.fext[2] * g.batch < (1ll << 31) - (1ll << 20);
     int err = vec ? phi_launch_advect_centered_vec(g, vel, ff, src, tmp, dt, nullptr, 0.f, s) : phi_launch_advect(g, vel, ff, -1, src, tmp, dt, s);
     if (err) return err;
     err = vec ? phi_launch_advect_centered_vec(g, vel, ff, tmp, dst, -dt, nullptr, 0.f, s) : phi_launch_advect(g, vel, ff, -1, tmp, dst, -dt, s);

@@ -245,7 +245,10 @@ int phicuda_advect_centered_f32(const PhiGrid* g, const PhiVBC* vbc, const float
     DGrid dg; DVec dv; DField ff;
     CHECK(phi_make_dgrid(g, &dg)); CHECK(make_vec(g, vbc, vel, &dv)); CHECK(phi_make_centered(g, fbc, &ff));
     if (!src || !dst || src == dst) { phi_set_error("advect: src and dst must be distinct non-NULL arrays"); return PHI_ERR_INVALID; }
-    if (!phi_scalar_kernels()) return cuda_fail(phi_launch_advect_centered_vec(dg, dv, ff, src, dst, dt, nullptr, 0.f, (cudaStream_t)stream), "advect_centered");
+    if (!phi_scalar_kernels()) {
+        const int e = phi_launch_advect_centered_vec(dg, dv, ff, src, dst, dt, nullptr, 0.f, (cudaStream_t)stream);
+        if (e != -100) return cuda_fail(e, "advect_centered");          // -100: arrays beyond 2^31 elements -> 64-bit scalar kernel
+    }
     return cuda_fail(phi_launch_advect(dg, dv, ff, -1, src, dst, dt, (cudaStream_t)stream), "advect_centered");
 }
 
@@ -260,11 +263,20 @@ int phicuda_advect_staggered_f32(const PhiGrid* g, const PhiVBC* vbc, const floa
     }
     if (!phi_scalar_kernels()) {      // all components in one launch: the velocity lines are loaded once and shared
         DVecOut out; for (int c = 0; c < 3; ++c) out.p[c] = c < g->dim ? dst[c] : nullptr;
-        return cuda_fail(phi_launch_advect_staggered_vec(dg, dv, df, out, dt, nullptr, nullptr, nullptr, (cudaStream_t)stream), "advect_staggered");
+        const int e = phi_launch_advect_staggered_vec(dg, dv, df, out, dt, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+        if (e != -100) return cuda_fail(e, "advect_staggered");
     }
     for (int c = 0; c < g->dim; ++c)
         CHECK(cuda_fail(phi_launch_advect(dg, dv, df.f[c], c, src[c], dst[c], dt, (cudaStream_t)stream), "advect_staggered"));
     return 0;
+}
+
+int phicuda_grid_sample_f32(const PhiGrid* g, const PhiBC* bc, const float* grid, const float* coords, int64_t npoints, float* out, void* stream)
+{
+    DGrid dg; DField f;
+    CHECK(phi_make_dgrid(g, &dg)); CHECK(phi_make_centered(g, bc, &f));
+    if (npoints < 0 || (npoints > 0 && (!grid || !coords || !out))) { phi_set_error("grid_sample: NULL argument"); return PHI_ERR_INVALID; }
+    return cuda_fail(phi_launch_grid_sample(dg, f, grid, coords, (long long)npoints, out, (cudaStream_t)stream), "grid_sample");
 }
 
 int phicuda_mac_cormack_centered_f32(const PhiGrid* g, const PhiVBC* vbc, const float* const vel[3],
@@ -431,7 +443,7 @@ int phicuda_plume_step_f32(const PhiGrid* g, const PhiVBC* vbc, const PhiBC* sbc
     cudaStream_t st = (cudaStream_t)stream;
     const bool has_inflow = inflow && sp->inflow_rate != 0.f;
     if (sp->static_scalar) {                // forced step: s is a stationary source field
-        if (phi_scalar_kernels()) {
+        if (phi_scalar_kernels() || (long long)farr > (1ll << 31) - (1ll << 20)) {
             CHECK(phicuda_advect_staggered_f32(g, vbc, v, vbc, v, vn, sp->dt, stream));
             CHECK(phicuda_add_buoyancy_f32(g, vbc, sbc, s, sp->buoyancy, sp->dt, vn, stream));
         } else {
@@ -439,7 +451,8 @@ int phicuda_plume_step_f32(const PhiGrid* g, const PhiVBC* vbc, const PhiBC* sbc
         }
         return project(g, vbc, vn, v, p, tmp, prm, result, workspace, workspace_bytes, sp->cg_start_event, sp->cg_stop_event, stream);
     }
-    if (phi_scalar_kernels()) {             // round-1 sequence, kept for A/B comparisons
+    const bool big = (long long)farr > (1ll << 31) - (1ll << 20);     // beyond 32-bit element offsets: 64-bit scalar kernels
+    if (phi_scalar_kernels() || big) {      // round-1 sequence, kept for A/B comparisons
         if (sp->mac_cormack) CHECK(phicuda_mac_cormack_centered_f32(g, vbc, v, sbc, s, s_new, tmp, sp->dt, 1.0f, stream));
         else                 CHECK(phicuda_advect_centered_f32(g, vbc, v, sbc, s, s_new, sp->dt, stream));
         if (has_inflow) CHECK(phicuda_axpy_centered_f32(g, sp->inflow_rate, inflow, s_new, stream));

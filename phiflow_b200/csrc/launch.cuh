@@ -25,6 +25,7 @@ int phi_launch_advect_centered_vec(const DGrid& g, const DVec& vel, const DField
                                    const float* add, float add_scale, cudaStream_t s);
 int phi_launch_advect_staggered_vec(const DGrid& g, const DVec& vel, const DVec& fld, const DVecOut& dst, float dt,
                                     const DField* sf, const float* sarr, const float bu[3], cudaStream_t s);
+int phi_launch_grid_sample(const DGrid& g, const DField& f, const float* grid, const float* coords, long long npoints, float* out, cudaStream_t s);
 bool phi_scalar_kernels();      // PHICUDA_SCALAR_KERNELS=1: diagnostics, forces the one-thread-per-sample kernels of round 1
 
 struct CgLaunch {

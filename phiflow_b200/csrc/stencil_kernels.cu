@@ -93,7 +93,7 @@ k_divergence(DGrid g, DVec v, DField cf, float* __restrict__ div, const float* _
     for (int c = 0; c < DIM; ++c) {
         const float lo = phi_fetch<DIM>(v.p[c], g, v.f[c], i.b, i.x, i.y, i.z);
         const float hi = phi_fetch<DIM>(v.p[c], g, v.f[c], i.b, i.x + (c == 0), i.y + (c == 1), i.z + (c == 2));
-        const float term = __fdiv_rn(hi - lo, g.dx[c]);
+        const float term = phi_div(hi - lo, g.dx[c], g.inv_dx[c]);
         acc = (c == 0) ? term : acc + term;
     }
     const long long o = phi_off(cf, i);
@@ -113,7 +113,7 @@ k_grad_sub(DGrid g, DVec vin, DVecOut v, DField pf, const float* __restrict__ p,
         if (!phi_in_range(vin.f[c], DIM, i.x, i.y, i.z)) continue;
         const float up = phi_fetch<DIM>(p, g, pf, i.b, i.x, i.y, i.z);
         const float lw = phi_fetch<DIM>(p, g, pf, i.b, i.x - (c == 0), i.y - (c == 1), i.z - (c == 2));
-        float grad = __fdiv_rn(up - lw, g.dx[c]);
+        float grad = phi_div(up - lw, g.dx[c], g.inv_dx[c]);
         if (accm) {     // hard_bcs = min of the two adjacent cells' accessibility (fluid.py:134)
             const float au = phi_fetch<DIM>(accm, g, af, i.b, i.x, i.y, i.z);
             const float al = phi_fetch<DIM>(accm, g, af, i.b, i.x - (c == 0), i.y - (c == 1), i.z - (c == 2));

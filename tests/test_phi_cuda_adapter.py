@@ -1,0 +1,302 @@
+"""
+Reference-side adapter (phiflow_b200/phi_cuda, row B1) against REAL phiml objects from the vendored PhiML 1.7.2
+(/root/reference/PhiML; skipped where it is absent, e.g. on the GPU box): boundary translation, named-dim layouts incl. the
+non-uniform staggered TensorStack, the eligibility matrix of SURVEY.md section 3.4, and the hot-path functions with phiml Tensors
+in and out.  There is no GPU here, so the compute engine is replaced by an oracle-backed stand-in with the SAME interface as
+phiflow_b200._ops (device arrays in, device arrays updated in place) - this file tests the plumbing around the C ABI, the
+kernels themselves are tested against the oracle in the -m gpu tests.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+PHIML = '/root/reference/PhiML'
+if not os.path.isdir(PHIML):
+    pytest.skip('vendored PhiML not available (reference tree absent)', allow_module_level=True)
+if PHIML not in sys.path:
+    sys.path.insert(0, PHIML)
+
+from phiml import math  # noqa: E402
+from phiml.math import extrapolation as E, spatial, batch, dual, channel  # noqa: E402
+
+from oracle import oracle_np as O  # noqa: E402
+from phiflow_b200 import _ops  # noqa: E402
+from phiflow_b200.phi_cuda import _adapter as A  # noqa: E402
+
+
+# ---- oracle-backed stand-in for phiflow_b200._ops (CPU tensors in the device layout) -------------------------------------
+class FakeOps:
+    Domain = _ops.Domain
+    cg_params = staticmethod(_ops.cg_params)
+    last = None
+
+    @staticmethod
+    def _geom(dom):
+        lower = (0.0,) * dom.dim
+        upper = tuple(dom.res[a] * dom.dx[a] for a in range(dom.dim))
+        return lower, upper
+
+    @classmethod
+    def make_incompressible(cls, dom, vspec, v, p, prm):
+        comps = dom.faces_to_numpy(v, vspec, squeeze=False)
+        p0 = dom.centered_to_numpy(p, squeeze=False)
+        outs, ps, infos = [], [], []
+        solver = O.cg_adaptive if prm.method == 1 else O.cg
+        for b in range(dom.batch):
+            vb = [c[b] for c in comps]
+            # same sequence as oracle.make_incompressible, with the solver the engine was asked for
+            div = O.divergence_staggered(vb, dom.dx, O.component_bcs(vspec, dom.dim))
+            if not O.is_flexible(vspec):
+                div = div - np.mean(div, dtype=np.float32)
+            Amat = O.poisson_matrix(dom.res, dom.dx, O.pressure_bc(vspec))
+            info = solver(Amat, div, p0[b], prm.rtol, prm.atol, prm.max_iter, None)
+            pb = info['x'].reshape(dom.res)
+            grad = O.gradient_faces(pb, dom.dx, O.pressure_bc(vspec), vspec)
+            outs.append([a - g for a, g in zip(vb, grad)]); ps.append(pb); infos.append(info)
+        new = dom.faces_from_numpy([np.stack([o[c] for o in outs]) for c in range(dom.dim)], vspec)
+        for c in range(dom.dim):
+            v[c].copy_(new[c])
+        p.copy_(dom.centered_from_numpy(np.stack(ps)))
+        rec = np.zeros(dom.batch, dtype=_ops._RESULT_DTYPE)
+        for b, info in enumerate(infos):
+            rec[b] = (info['iterations'], int(info['converged']), int(info['diverged']), info['residual_sq'], info['tol_sq'], 0.0)
+        cls.last = rec
+
+    @classmethod
+    def read_results(cls, dom):
+        return cls.last
+
+    @classmethod
+    def advect_staggered(cls, dom, vspec, v, fspec, f, dt):
+        lower, upper = cls._geom(dom)
+        vc, fc = dom.faces_to_numpy(v, vspec, squeeze=False), dom.faces_to_numpy(f, fspec, squeeze=False)
+        out = [O.semi_lagrangian_staggered([c[b] for c in fc], fspec, [c[b] for c in vc], vspec, dom.res, lower, upper, dt) for b in range(dom.batch)]
+        return dom.faces_from_numpy([np.stack([o[c] for o in out]) for c in range(dom.dim)], fspec)
+
+    @classmethod
+    def advect_centered(cls, dom, vspec, v, sspec, s, dt):
+        lower, upper = cls._geom(dom)
+        vc, sc = dom.faces_to_numpy(v, vspec, squeeze=False), dom.centered_to_numpy(s, squeeze=False)
+        return dom.centered_from_numpy(np.stack([O.semi_lagrangian_centered(sc[b], sspec, [c[b] for c in vc], vspec, lower, upper, dt)
+                                                 for b in range(dom.batch)]))
+
+    @classmethod
+    def laplace(cls, dom, spec, x):
+        a = dom.centered_to_numpy(x, squeeze=False)
+        return dom.centered_from_numpy(np.stack([O.laplace(a[b], dom.dx, spec) for b in range(dom.batch)]))
+
+    @classmethod
+    def divergence(cls, dom, vspec, v):
+        vc = dom.faces_to_numpy(v, vspec, squeeze=False)
+        return dom.centered_from_numpy(np.stack([O.divergence_staggered([c[b] for c in vc], dom.dx, O.component_bcs(vspec, dom.dim))
+                                                 for b in range(dom.batch)]))
+
+
+@pytest.fixture()
+def fake_engine(monkeypatch):
+    monkeypatch.setattr(A, 'ENGINE', FakeOps)
+    monkeypatch.setattr(A, 'DEVICE', 'cpu')
+    return FakeOps
+
+
+# ---- (i) boundary translation ---------------------------------------------------------------------------------------------------
+def test_extrapolation_translation_table():
+    dims = ('x', 'y')
+    assert A.to_spec(E.ZERO, dims) == ((0.0, 0.0), (0.0, 0.0))
+    assert A.to_spec(E.ONE, dims) == ((1.0, 1.0), (1.0, 1.0))
+    assert A.to_spec(E.PERIODIC, dims) == (('periodic', 'periodic'),) * 2
+    assert A.to_spec(E.ZERO_GRADIENT, dims) == (('zg', 'zg'),) * 2
+    assert E.BOUNDARY is E.ZERO_GRADIENT
+    assert A.to_spec(E.ConstantExtrapolation(2.5), ('x', 'y', 'z')) == ((2.5, 2.5),) * 3
+    # combine_sides (tests/commit/physics/test_fluid.py:50-53)
+    mixed = E.combine_sides(x=E.BOUNDARY, y=(E.ZERO, E.BOUNDARY))
+    assert A.to_spec(mixed, dims) == (('zg', 'zg'), (0.0, 'zg'))
+    assert A.to_vspec(mixed, dims) == (('zg', 'zg'), (0.0, 'zg'))
+    per_wall = E.combine_sides(x=E.PERIODIC, y=E.ZERO)
+    assert A.to_spec(per_wall, dims) == (('periodic', 'periodic'), (0.0, 0.0))
+    # vector constants: one spec per component (inflow boundary: different constants, same kinds)
+    inflow = E.ConstantExtrapolation(math.tensor([1.0, 0.0], channel(vector='x,y')))
+    assert A.to_vspec(inflow, dims) == [((1.0, 1.0), (1.0, 1.0)), ((0.0, 0.0), (0.0, 0.0))]
+    both = E.combine_sides(x=(inflow, E.BOUNDARY), y=E.ZERO)
+    assert A.to_vspec(both, dims) == [((1.0, 'zg'), (0.0, 0.0)), ((0.0, 'zg'), (0.0, 0.0))]
+    # faces stored per side follow valid_outer_faces (extrapolation.py:57-62, tests/commit/field/test__grid.py:25-37)
+    assert A.stored_face_counts(A.to_vspec(mixed, dims), (16, 20)) == [(17, 20), (16, 20)]
+    for d, ext in (('x', E.ZERO), ('x', E.PERIODIC), ('x', E.BOUNDARY)):
+        lo, hi = ext.valid_outer_faces(d)
+        spec = A.to_vspec(ext, dims)
+        assert _ops.stored_faces(spec, 0) == (lo, hi)
+
+
+@pytest.mark.parametrize('ext', [E.SYMMETRIC, E.REFLECT, E.NONE, E.ANTISYMMETRIC if hasattr(E, 'ANTISYMMETRIC') else E.SYMMETRIC])
+def test_unsupported_boundaries_are_not_eligible(ext):
+    with pytest.raises(A.NotEligible):
+        A.to_spec(ext, ('x', 'y'))
+    assert A.eligible(('x', 'y'), ext) is not None
+
+
+def test_periodic_on_one_side_only_is_rejected():
+    with pytest.raises(A.NotEligible):
+        A.to_spec(E.combine_sides(x=(E.PERIODIC, E.ZERO), y=E.ZERO), ('x', 'y'))
+
+
+# ---- (iii) eligibility matrix ------------------------------------------------------------------------------
+def test_eligibility_matrix():
+    dims = ('x', 'y', 'z')
+    assert A.eligible(dims, E.ZERO, solve_method='CG') is None
+    assert A.eligible(dims, E.PERIODIC, solve_method='auto') is None
+    assert A.eligible(dims, E.combine_sides(x=E.PERIODIC, y=E.ZERO, z=(E.ZERO, E.BOUNDARY)), solve_method='CG-adaptive') is None
+    assert 'order' in A.eligible(dims, E.ZERO, order=4)
+    assert 'solver' in A.eligible(dims, E.ZERO, solve_method='biCG-stab(2)')
+    assert 'solver' in A.eligible(dims, E.ZERO, solve_method='scipy-direct')
+    assert 'obstacles' in A.eligible(dims, E.ZERO, obstacles=[object()])
+    assert 'active' in A.eligible(dims, E.ZERO, active=object())
+    assert 'CenteredGrid' in A.eligible(dims, E.ZERO, staggered=False)
+    assert 'preconditioned' in A.eligible(dims, E.ZERO, preconditioner='ilu')
+    assert '1-D' in A.eligible(('x',), E.ZERO)
+    assert 'non-uniform' in A.eligible(dims, E.ZERO, uniform=False)
+    with math.precision(64):                      # Taylor_Green / Kolmogorov notebooks: never silently downcast
+        assert 'precision 64' in A.eligible(dims, E.ZERO)
+    assert A.eligible(dims, E.ZERO) is None
+
+
+# ---- (ii) layouts -------------------------------------------------------------------------------------------------------------------
+def _staggered_values(rng, res, vspec, dims, batch_shape=None):
+    shapes = O.staggered_shapes(res, vspec)
+    comps, arrays = [], []
+    for c, s in enumerate(shapes):
+        pre = () if batch_shape is None else batch_shape.sizes
+        a = rng.standard_normal(pre + s).astype(np.float32)
+        arrays.append(a)
+        shape = spatial(**dict(zip(dims, s)))
+        comps.append(math.tensor(a, (batch_shape & shape) if batch_shape is not None else shape))
+    return math.stack(comps, dual(vector=dims)), arrays
+
+
+def test_nonuniform_staggered_stack_roundtrip(fake_engine):
+    """combine_sides(x=BOUNDARY, y=(ZERO, BOUNDARY)): components of 17x20 and 16x20 faces form a non-uniform TensorStack that
+    has no single native array - it is exported per component and rebuilt with math.stack(..., dual(vector))."""
+    dims, res = ('x', 'y'), (16, 20)
+    ext = E.combine_sides(x=E.BOUNDARY, y=(E.ZERO, E.BOUNDARY))
+    vspec = A.to_vspec(ext, dims)
+    bshape = batch(b=3)
+    values, arrays = _staggered_values(np.random.default_rng(0), res, vspec, dims, bshape)
+    assert not values.shape.is_uniform
+    comps = A.split_components(values, dims)
+    assert [tuple(c.shape.get_size(d) for d in dims) for c in comps] == [(17, 20), (16, 20)]
+    dom = _ops.Domain(res, (1.0, 1.0), 3, vbc=vspec, device='cpu')
+    dev = A.pull_staggered(dom, comps, vspec, bshape, dims)
+    # device layout: (batch, y, x), x contiguous; y component starts at face 1 along y (the wall face 0 is not stored)
+    assert dev[0].shape == (3, dom.fext[1], dom.fext[0])
+    np.testing.assert_array_equal(dev[0][1, :20, :17].numpy(), arrays[0][1].T)
+    np.testing.assert_array_equal(dev[1][2, 1:21, :16].numpy(), arrays[1][2].T)
+    assert float(dev[1][:, 0].abs().max()) == 0.0
+    back = A.push_staggered(dom, dev, vspec, bshape, dims)
+    assert back.shape.names == values.shape.names or set(back.shape.names) == set(values.shape.names)
+    for d, a in zip(dims, arrays):
+        np.testing.assert_array_equal(back[{'~vector': d}].numpy(('b',) + dims), a)
+    # wrong face counts are refused (e.g. values built for another boundary)
+    with pytest.raises(A.NotEligible):
+        A.pull_staggered(dom, comps, A.to_vspec(E.ZERO, dims), bshape, dims)
+
+
+def test_centered_roundtrip_keeps_dim_names_and_order(fake_engine):
+    dims, res = ('x', 'y', 'z'), (5, 4, 3)
+    a = np.arange(2 * 5 * 4 * 3, dtype=np.float32).reshape(2, 5, 4, 3)
+    t = math.tensor(a, batch(batch=2) & spatial(x=5, y=4, z=3))
+    dom = _ops.Domain(res, (1.0,) * 3, 2, device='cpu')
+    dev = A.pull_centered(dom, t, t.shape.batch, dims)
+    assert dev.shape == (2, 3, 4, 8)                         # z, y, x with x padded to a multiple of 4
+    assert float(dev[1, 2, 3, 4]) == a[1, 4, 3, 2]           # reference order is x outermost, z contiguous
+    back = A.push_centered(dom, dev, t.shape.batch, dims)
+    np.testing.assert_array_equal(back.numpy('batch,x,y,z'), a)
+    # a tensor stored in another dim order gives the same device array
+    t2 = math.tensor(np.transpose(a, (0, 3, 1, 2)), batch(batch=2) & spatial(z=3, x=5, y=4))
+    assert torch.equal(A.pull_centered(dom, t2, t2.shape.batch, dims), dev)
+
+
+# ---- (iv) hot-path functions: phiml Tensors in, phiml Tensors out ----------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['zero', 'boundary', 'periodic', 'mixed'])
+def test_make_incompressible_with_phiml_tensors(fake_engine, name):
+    """The cases of tests/commit/physics/test_fluid.py:38-53 (16x20 StaggeredGrid) on values / extrapolation / dx as a Field holds
+    them.  Checks: named dims and face counts of the result, pressure on the cell grid, divergence-free by the REFERENCE's own
+    arithmetic (phiml pad + forward differences, phi/field/_field_math.py:617-626)."""
+    dims, res = ('x', 'y'), (16, 20)
+    ext = {'zero': E.ZERO, 'boundary': E.BOUNDARY, 'periodic': E.PERIODIC, 'mixed': E.combine_sides(x=E.BOUNDARY, y=(E.ZERO, E.BOUNDARY))}[name]
+    dx = {'x': 100.0 / 16, 'y': 100.0 / 20}
+    vspec = A.to_vspec(ext, dims)
+    values, arrays = _staggered_values(np.random.default_rng(3), res, vspec, dims, batch(b=2))
+    new_values, pressure, info = A.make_incompressible(values, ext, dx, dims, res, method='CG', rel_tol=1e-5, abs_tol=1e-5)
+    assert set(pressure.shape.names) == {'b', 'x', 'y'} and pressure.shape.get_size('x') == 16 and pressure.shape.get_size('y') == 20
+    assert info['converged'].all() and not info['diverged'].any() and (info['iterations'] > 0).all()
+    for c, d in enumerate(dims):
+        comp = new_values[{'~vector': d}]
+        assert tuple(comp.shape.get_size(k) for k in dims) == arrays[c].shape[1:]
+    # divergence with the reference's arithmetic: bake the boundary faces with math.pad, forward differences
+    div = 0
+    for c, d in enumerate(dims):
+        comp = new_values[{'~vector': d}]
+        lo, hi = ext.valid_outer_faces(d)
+        baked = math.pad(comp, {d: (0 if lo else 1, 0 if hi else 1)}, ext[{'vector': d}] if name != 'mixed' else ext)
+        div = div + (baked[{d: slice(1, None)}] - baked[{d: slice(None, -1)}]) / dx[d]
+    assert float(np.abs(div.numpy(div.shape.names)).max()) < 5e-5 * max(1.0, float(max(np.abs(a).max() for a in arrays)))
+    # and the fall-through contract: ineligible requests raise NotEligible, nothing is computed
+    with pytest.raises(A.NotEligible):
+        A.make_incompressible(values, ext, dx, dims, res, method='biCG-stab(2)')
+    with math.precision(64):
+        with pytest.raises(A.NotEligible):
+            A.make_incompressible(values, ext, dx, dims, res, method='CG')
+
+
+def test_semi_lagrangian_and_stencils_with_phiml_tensors(fake_engine):
+    dims, res = ('x', 'y'), (12, 10)
+    ext = E.ZERO
+    dx = {'x': 1.0, 'y': 0.5}
+    vspec = A.to_vspec(ext, dims)
+    values, arrays = _staggered_values(np.random.default_rng(4), res, vspec, dims)
+    out = A.semi_lagrangian_staggered(values, ext, values, ext, dx, dims, res, 0.3)
+    ref = O.semi_lagrangian_staggered(arrays, vspec, arrays, vspec, res, (0.0, 0.0), (12.0, 5.0), 0.3)
+    for c, d in enumerate(dims):
+        np.testing.assert_allclose(out[{'~vector': d}].numpy(dims), ref[c], atol=1e-6)
+    s = np.random.default_rng(5).standard_normal(res).astype(np.float32)
+    st = math.tensor(s, spatial(x=12, y=10))
+    adv = A.semi_lagrangian_centered(st, E.BOUNDARY, values, ext, dx, dims, res, 0.3)
+    np.testing.assert_allclose(adv.numpy(dims), O.semi_lagrangian_centered(s, O.uniform_bc(2, 'zg'), arrays, vspec, (0.0, 0.0), (12.0, 5.0), 0.3), atol=1e-6)
+    # laplace against the vendored phiml itself (PhiML/phiml/math/_nd.py:825-861)
+    lap = A.laplace(st, E.ZERO_GRADIENT, dx, dims, res)
+    ref_lap = math.laplace(st, dx=math.vec(x=1.0, y=0.5), padding=E.ZERO_GRADIENT)
+    np.testing.assert_allclose(lap.numpy(dims), ref_lap.numpy(dims), atol=2e-5)
+    div = A.divergence(values, ext, dx, dims, res)
+    np.testing.assert_allclose(div.numpy(dims), O.divergence_staggered(arrays, (1.0, 0.5), O.component_bcs(vspec, 2)), atol=1e-6)
+
+
+# ---- the Backend subclass -----------------------------------------------------------------------------------------------------------
+def test_backend_registration_and_fall_through(fake_engine):
+    from phiml.backend import Backend, BACKENDS
+    from phiflow_b200.phi_cuda._backend import get_backend, PhiCudaBackend, PoissonOperator
+    b = get_backend()
+    assert isinstance(b, PhiCudaBackend) and b in BACKENDS and b.name == 'phicuda'
+    assert [x.name for x in BACKENDS].count('phicuda') == 1
+    assert b.supports(Backend.grid_sample) and b.supports(Backend.linear_solve)
+    f = lambda x: x + 1
+    assert b.jit_compile(f) is f                         # ctypes launches are never traced
+    # unknown linear operators go to the stock torch implementation
+    mat = torch.tensor([[4.0, 1.0], [1.0, 3.0]])
+    y = torch.tensor([[1.0, 2.0]])
+    res = b.linear_solve('CG', mat, y, torch.zeros_like(y), np.array([1e-6]), np.array([1e-6]), np.array([[100]]), None, None)
+    np.testing.assert_allclose(np.asarray(res.x)[0], np.linalg.solve(mat.numpy(), y.numpy()[0]), atol=1e-4)
+    # grid_sample on tensors the fast path does not own (CPU) -> exactly what the stock torch backend answers (values or
+    # NotImplemented, after which phiml runs its own fallback, _ops.py:983-1015)
+    from phiml.backend.torch._torch_backend import TorchBackend
+    grid = torch.arange(12, dtype=torch.float32).reshape(1, 4, 3, 1)
+    pts = torch.tensor([[[0.5, 0.0], [1.5, 1.0], [2.25, 1.5]]])
+    out, stock = b.grid_sample(grid, pts, 'boundary'), TorchBackend.grid_sample(b, grid, pts, 'boundary')
+    if stock is NotImplemented:
+        assert out is NotImplemented
+    else:
+        np.testing.assert_allclose(np.asarray(out).ravel(), np.asarray(stock).ravel(), atol=1e-6)
+        np.testing.assert_allclose(np.asarray(out).ravel(), [1.5, 5.5, 8.25], atol=1e-5)
+    with pytest.raises(NotImplementedError):
+        b.linear_solve('biCG-stab(2)', PoissonOperator((4, 4), (1.0, 1.0), A.to_vspec(E.ZERO, ('x', 'y'))), y, y, [1e-5], [1e-5], np.array([[10]]), None, None)
