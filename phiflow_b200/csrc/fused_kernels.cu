@@ -400,7 +400,7 @@ k_advect_centered_vec(const __grid_constant__ DGrid g, const __grid_constant__ D
 // Staggered field, all components in one launch: dst_c = interp(src_c, face_c - dt v(face_c)) [+ dt * buoyancy_c]
 //   buoyancy_c = (s * b_c)[upper cell] * 0.5 + (s * b_c)[lower cell] * 0.5      (sample_grid_at_faces)
 template <int DIM, bool BUOY>
-__global__ void __launch_bounds__(FK_THREADS, 3)
+__global__ void __launch_bounds__(FK_THREADS, 4)
 k_advect_staggered_vec(const __grid_constant__ DGrid g, const __grid_constant__ DVec vel, const __grid_constant__ DVec fld,
                        const __grid_constant__ DVecOut dst, float dt, const __grid_constant__ DField sf, const float* __restrict__ s,
                        float b0, float b1, float b2)

@@ -94,13 +94,15 @@ def test_cg_fast_variant(res, vname):
     rtol = 1e-3
     with ring_nzc(12 if multi else 0):
         dom = ops.Domain(res, DX, batch, vbc=vbc)
-        prm = ops.cg_params(vbc, rtol=rtol, atol=1e-5, max_iter=1000)
+        # (the closed 512 x 8 x 8 box with dx = (0.5, 0.25, 2) needs > 1000 iterations in the oracle as well)
+        prm = ops.cg_params(vbc, rtol=rtol, atol=1e-5, max_iter=5000)
         got = dom.centered_to_numpy(ops.cg_poisson(dom, vbc, dom.centered_from_numpy(rhs), None, prm), squeeze=False)
         assert_fast(_lib.KERNEL_CG_RING, multi)
     info = ops.read_results(dom)
     for b in range(batch):
         y = rhs[b] - rhs[b].mean()
-        ref = O.cg(A, y, np.zeros(res, np.float32), rtol, 1e-5, 1000, None)
+        ref = O.cg(A, y, np.zeros(res, np.float32), rtol, 1e-5, 5000, None)
+        assert ref['converged']
         assert info['converged'][b] == 1 and info['diverged'][b] == 0
         assert abs(int(info['iterations'][b]) - ref['iterations']) <= max(2, ref['iterations'] // 10), (info['iterations'][b], ref['iterations'])
         r = y.ravel() - A.dot(got[b].ravel().astype(np.float64))
