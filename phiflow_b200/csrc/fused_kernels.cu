@@ -26,18 +26,22 @@
 #define FK_WARPS 8
 #define FK_THREADS (FK_WARPS * 32)
 
+// A resolved line is an element offset relative to the array pointer (which addresses the first OWNED plane: offsets of slab
+// halo planes are negative) or a constant ghost line, marked by this sentinel.
+#define FK_CONST_LINE (-(1ll << 62))
+
 // value at index x of a resolved line; x outside the stored range follows the boundary (same resolution order as phi_fetch)
 __device__ __forceinline__ float fk_ldx(const float* __restrict__ a, const RowRef<3>& r, const DField& f, int x)
 {
     if (x < f.lo[0] || x > f.hi[0]) { float c; if (!phi_resolve(x, f, 0, c)) return c; }
-    if (r.off < 0) return r.cval;
+    if (r.off == FK_CONST_LINE) return r.cval;
     return __ldg(a + r.off + x);
 }
 
 template <int DIM>
 __device__ __forceinline__ RowRef<3> fk_row(const DGrid& g, const DField& f, int b, int y, int z)
 {
-    RowRef<3> r; r.cval = 0.f; r.off = -1;
+    RowRef<3> r; r.cval = 0.f; r.off = FK_CONST_LINE;
     if (!phi_resolve(y, f, 1, r.cval)) return r;
     if (DIM == 3) { if (!phi_resolve(z, f, 2, r.cval)) return r; } else z = 0;
     r.off = (long long)b * f.sb + (long long)z * f.sz + (long long)y * f.sy;
@@ -47,7 +51,7 @@ __device__ __forceinline__ RowRef<3> fk_row(const DGrid& g, const DField& f, int
 // four consecutive values x0 .. x0+3 of a resolved line (x0 % 4 == 0).  Fast when all four are stored values.
 __device__ __forceinline__ float4 fk_ld4(const float* __restrict__ a, const RowRef<3>& r, const DField& f, int x0)
 {
-    if (x0 >= f.lo[0] && x0 + 3 <= f.hi[0] && r.off >= 0) return __ldg(reinterpret_cast<const float4*>(a + r.off + x0));
+    if (x0 >= f.lo[0] && x0 + 3 <= f.hi[0] && r.off != FK_CONST_LINE) return __ldg(reinterpret_cast<const float4*>(a + r.off + x0));
     return make_float4(fk_ldx(a, r, f, x0), fk_ldx(a, r, f, x0 + 1), fk_ldx(a, r, f, x0 + 2), fk_ldx(a, r, f, x0 + 3));
 }
 
@@ -80,16 +84,27 @@ k_div_vec(const __grid_constant__ DGrid g, const __grid_constant__ DVec v, const
     const int lane = threadIdx.x & 31;
     const int x0 = L.x0;
     const bool in_line = x0 < g.n[0];
-    const RowRef<3> rx = fk_row<DIM>(g, v.f[0], L.b, L.y, L.z);
-    const RowRef<3> ry0 = fk_row<DIM>(g, v.f[1], L.b, L.y, L.z), ry1 = fk_row<DIM>(g, v.f[1], L.b, L.y + 1, L.z);
+    // lines whose y / z neighbours are all stored lines of every component need no boundary resolution (warp-uniform)
+    const bool interior = L.y >= max(v.f[0].lo[1], v.f[1].lo[1]) && L.y + 1 <= min(v.f[0].hi[1], v.f[1].hi[1])
+                          && (DIM == 2 || (L.y >= v.f[2].lo[1] && L.y <= v.f[2].hi[1]
+                                           && L.z >= max(max(v.f[0].lo[2], v.f[1].lo[2]), v.f[2].lo[2])
+                                           && L.z + 1 <= min(min(v.f[0].hi[2], v.f[1].hi[2]), v.f[2].hi[2])));
+    RowRef<3> rx, ry0, ry1, rz0, rz1;
+    if (interior) {
+        const long long base = (long long)L.b * v.f[0].sb + (long long)L.z * v.f[0].sz + (long long)L.y * v.f[0].sy;
+        rx.off = base; ry0.off = base; ry1.off = base + v.f[0].sy; rz0.off = base; rz1.off = base + v.f[0].sz;
+        rx.cval = ry0.cval = ry1.cval = rz0.cval = rz1.cval = 0.f;
+    } else {
+        rx = fk_row<DIM>(g, v.f[0], L.b, L.y, L.z);
+        ry0 = fk_row<DIM>(g, v.f[1], L.b, L.y, L.z); ry1 = fk_row<DIM>(g, v.f[1], L.b, L.y + 1, L.z);
+        rz0 = rx; rz1 = rx;
+        if (DIM == 3) { rz0 = fk_row<DIM>(g, v.f[2], L.b, L.y, L.z); rz1 = fk_row<DIM>(g, v.f[2], L.b, L.y, L.z + 1); }
+    }
     float4 ax = f4_splat(0.f), ay0 = ax, ay1 = ax, az0 = ax, az1 = ax;
     if (in_line) {
         ax = fk_ld4(v.p[0], rx, v.f[0], x0);
         ay0 = fk_ld4(v.p[1], ry0, v.f[1], x0); ay1 = fk_ld4(v.p[1], ry1, v.f[1], x0);
-        if (DIM == 3) {
-            const RowRef<3> rz0 = fk_row<DIM>(g, v.f[2], L.b, L.y, L.z), rz1 = fk_row<DIM>(g, v.f[2], L.b, L.y, L.z + 1);
-            az0 = fk_ld4(v.p[2], rz0, v.f[2], x0); az1 = fk_ld4(v.p[2], rz1, v.f[2], x0);
-        }
+        if (DIM == 3) { az0 = fk_ld4(v.p[2], rz0, v.f[2], x0); az1 = fk_ld4(v.p[2], rz1, v.f[2], x0); }
     }
     float nx = __shfl_down_sync(0xffffffffu, ax.x, 1);                      // v_x[x0 + 4]
     if (in_line && (lane == 31 || x0 + 4 >= g.n[0])) nx = fk_ldx(v.p[0], rx, v.f[0], x0 + 4);
@@ -132,7 +147,11 @@ k_gradsub_vec(const __grid_constant__ DGrid g, const __grid_constant__ DVec vin,
     const int lane = threadIdx.x & 31;
     const int x0 = L.x0;
     const bool in_line = x0 < g.fext[0];
-    const RowRef<3> r0 = fk_row<DIM>(g, pf, L.b, L.y, L.z);
+    // p lines (y, z), (y - 1, z), (y, z - 1) are all stored lines: no boundary resolution (warp-uniform)
+    const bool interior = L.y >= 1 && L.y <= pf.hi[1] && (DIM == 2 || (L.z >= 1 && L.z <= pf.hi[2]));
+    RowRef<3> r0;
+    if (interior) { r0.off = (long long)L.b * pf.sb + (long long)L.z * pf.sz + (long long)L.y * pf.sy; r0.cval = 0.f; }
+    else r0 = fk_row<DIM>(g, pf, L.b, L.y, L.z);
     float4 pc = f4_splat(0.f);
     if (in_line) pc = fk_ld4(p, r0, pf, x0);
     float pl = __shfl_up_sync(0xffffffffu, pc.w, 1);                         // p[x0 - 1]
@@ -156,7 +175,8 @@ k_gradsub_vec(const __grid_constant__ DGrid g, const __grid_constant__ DVec vin,
     {   // y component
         const DField& f = vin.f[1];
         if (L.y >= f.lo[1] && L.y <= f.hi[1] && (DIM == 2 || L.z < g.n[2])) {
-            const RowRef<3> rm = fk_row<DIM>(g, pf, L.b, L.y - 1, L.z);
+            RowRef<3> rm = r0;
+            if (interior) rm.off = r0.off - pf.sy; else rm = fk_row<DIM>(g, pf, L.b, L.y - 1, L.z);
             const float4 pm = fk_ld4(p, rm, pf, x0);
             float4 a = *reinterpret_cast<const float4*>(vin.p[1] + off);
             a.x -= phi_div(pc.x - pm.x, dy, iy); a.y -= phi_div(pc.y - pm.y, dy, iy);
@@ -168,7 +188,8 @@ k_gradsub_vec(const __grid_constant__ DGrid g, const __grid_constant__ DVec vin,
     if (DIM == 3) {   // z component
         const DField& f = vin.f[2];
         if (L.z >= f.lo[2] && L.z <= f.hi[2] && L.y < g.n[1]) {
-            const RowRef<3> rm = fk_row<DIM>(g, pf, L.b, L.y, L.z - 1);
+            RowRef<3> rm = r0;
+            if (interior) rm.off = r0.off - pf.sz; else rm = fk_row<DIM>(g, pf, L.b, L.y, L.z - 1);
             const float4 pm = fk_ld4(p, rm, pf, x0);
             float4 a = *reinterpret_cast<const float4*>(vin.p[2] + off);
             a.x -= phi_div(pc.x - pm.x, dz, iz); a.y -= phi_div(pc.y - pm.y, dz, iz);
@@ -253,11 +274,51 @@ __device__ __noinline__ float fk_interp_slow(const float* __restrict__ a, const 
     return acc;
 }
 
+// neighbour pair (i, i + 1) of one axis mapped onto stored indices: PERIODIC wraps, ZERO_GRADIENT clamps, slab halo planes are
+// stored values; false when a neighbour is a constant ghost (-> fk_interp_slow)
+__device__ __forceinline__ bool fk_pair(const DField& f, int a, int i, int& i0, int& i1)
+{
+    float c;
+    i0 = i; i1 = i + 1;
+    return phi_resolve(i0, f, a, c) && phi_resolve(i1, f, a, c);
+}
+
+// middle tier: some neighbour lies across a periodic / zero-gradient / slab boundary - no constants involved.  Same weights
+// and summation order as fk_interp_inside.
+template <int DIM>
+__device__ __noinline__ float fk_interp_wrapped(const float* __restrict__ a, const DGrid* gp, const DField* fp, int b,
+                                                int i0, int i1, int i2, float tx, float ty, float tz)
+{
+    const DField& f = *fp;
+    int x0, x1, y0, y1, z0 = 0, z1 = 0;
+    bool ok = fk_pair(f, 0, i0, x0, x1) && fk_pair(f, 1, i1, y0, y1);
+    if (DIM == 3) ok = ok && fk_pair(f, 2, i2, z0, z1);
+    if (!ok) return fk_interp_slow<DIM>(a, gp, fp, b, i0, i1, i2, tx, ty, tz);
+    const int sy = (int)f.sy, sz = (int)f.sz;
+    const float* p = a + (long long)b * f.sb;
+    const int r00 = z0 * sz + y0 * sy, r01 = z0 * sz + y1 * sy;
+    const float n00 = __ldg(p + r00 + x0), n10 = __ldg(p + r00 + x1), n01 = __ldg(p + r01 + x0), n11 = __ldg(p + r01 + x1);
+    float acc = 0.f;
+    if (DIM == 3) {
+        const int r10 = z1 * sz + y0 * sy, r11 = z1 * sz + y1 * sy;
+        const float m00 = __ldg(p + r10 + x0), m10 = __ldg(p + r10 + x1), m01 = __ldg(p + r11 + x0), m11 = __ldg(p + r11 + x1);
+        const float w00 = (1.f - tx) * (1.f - ty), w01 = (1.f - tx) * ty, w10 = tx * (1.f - ty), w11 = tx * ty;
+        acc += n00 * (w00 * (1.f - tz)); acc += m00 * (w00 * tz);
+        acc += n01 * (w01 * (1.f - tz)); acc += m01 * (w01 * tz);
+        acc += n10 * (w10 * (1.f - tz)); acc += m10 * (w10 * tz);
+        acc += n11 * (w11 * (1.f - tz)); acc += m11 * (w11 * tz);
+    } else {
+        acc += n00 * ((1.f - tx) * (1.f - ty)); acc += n01 * ((1.f - tx) * ty);
+        acc += n10 * (tx * (1.f - ty)); acc += n11 * (tx * ty);
+    }
+    return acc;
+}
+
 template <int DIM>
 __device__ __forceinline__ float fk_interp(const float* __restrict__ a, const DGrid& g, const DField& f, int b, const FkLookup& L)
 {
     if (fk_inside<DIM>(f, L)) return fk_interp_inside<DIM>(a, f, b, L);
-    return fk_interp_slow<DIM>(a, &g, &f, b, L.i[0], L.i[1], L.i[2], L.t[0], L.t[1], L.t[2]);
+    return fk_interp_wrapped<DIM>(a, &g, &f, b, L.i[0], L.i[1], L.i[2], L.t[0], L.t[1], L.t[2]);
 }
 
 #define FK_XCHUNKS 4        // a warp walks 4 chunks of 32 cells of its line
@@ -450,9 +511,10 @@ k_advect_staggered_vec(const __grid_constant__ DGrid g, const __grid_constant__ 
         // (the lower x neighbour of the buoyancy source is wrapped / clamped below; a constant x boundary of s needs xb >= 1)
         const bool fast = rows_ok && X.fast && xb + 32 <= n0 && (!BUOY || (s_fast && (b0 == 0.f || sf.klo[0] != PHI_BC_CONST || xb >= 1)));
         float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-        const bool st0 = on0 && x >= fld.f[0].lo[0] && x <= fld.f[0].hi[0];
-        const bool st1 = on1 && x >= fld.f[1].lo[0] && x <= fld.f[1].hi[0];
-        const bool st2 = on2 && x >= fld.f[2].lo[0] && x <= fld.f[2].hi[0];
+        // a fast chunk lies inside the stored x range of every component, so its store flags are warp-uniform
+        const bool st0 = on0 && (fast || (x >= fld.f[0].lo[0] && x <= fld.f[0].hi[0]));
+        const bool st1 = on1 && (fast || (x >= fld.f[1].lo[0] && x <= fld.f[1].hi[0]));
+        const bool st2 = on2 && (fast || (x >= fld.f[2].lo[0] && x <= fld.f[2].hi[0]));
         if (fast) {                                                // warp-uniform: straight-line code, 32-bit offsets
             const float A0 = __ldg(vx + rA0 + X.xo), A1 = __ldg(vx + rA1 + X.xo);
             const float B0 = __ldg(vy + rB0 + X.xo), B1 = __ldg(vy + rB1 + X.xo);
