@@ -195,6 +195,9 @@ int phicuda_comm_destroy(PhiComm* comm);
 /* g describes the LOCAL slab (boundary kind PHI_BC_HALO on interior slab faces); x must carry valid halo planes. */
 int phicuda_cg_poisson_dist_f32(const PhiGrid* g, const PhiVBC* vbc, const float* rhs, float* x,
                                 const PhiCgParams* prm, PhiCgResult* result, PhiComm* comm, void* stream);
+/* N4 on z-slabs: the same with static obstacles; `accessible` carries valid halo planes (exchanged once, the mask is static). */
+int phicuda_cg_poisson_dist_masked_f32(const PhiGrid* g, const PhiVBC* vbc, const float* rhs, float* x, const float* accessible,
+                                       const PhiCgParams* prm, PhiCgResult* result, PhiComm* comm, void* stream);
 
 /* ---- A1  fluid.make_incompressible (phi/physics/fluid.py:94-162), no obstacles, order 2, staggered ------------------
  * div scratch: one centred array.  Equivalent to divergence + cg_poisson + grad_sub on the same stream. */
@@ -206,8 +209,14 @@ int phicuda_make_incompressible_f32(const PhiGrid* g, const PhiVBC* vbc, float* 
  * accessible: centred mask, 1 in fluid cells, 0 inside obstacles (`~union(obstacle geometries)` sampled at cell centres).
  * make_incompressible_masked = divergence * active, CG on masked_laplace (faces touching an obstacle carry no flux,
  * obstacle cells are identity rows), v -= hard_bcs * grad p.  The caller applies apply_boundary_conditions first
- * (v *= 1 - obstacle mask at faces: phicuda_mul_faces_f32).  Runs on the register-marching CG kernel. */
+ * (v *= 1 - obstacle mask at faces: phicuda_mul_faces_f32).  The solve runs on the TMA-ring kernel with the mask staged as an
+ * extra haloed array (k_cg_ring<..., MASK>; 5 lines per tile line and stage instead of 4); grids whose lines do not fit the
+ * ring fall back to the register-marching kernel. */
 int phicuda_mul_faces_f32(const PhiGrid* g, const PhiVBC* vbc, float* const v[3], const float* const mask[3], void* stream);
+/* the two stencil pieces of the masked projection on their own (z-slab runs exchange halo planes between them):
+ * div = divergence(v) * accessible;   v -= hard_bcs * grad p, hard_bcs = min of the two adjacent cells' accessibility */
+int phicuda_divergence_masked_f32(const PhiGrid* g, const PhiVBC* vbc, const float* const v[3], const float* accessible, float* div, void* stream);
+int phicuda_grad_sub_masked_f32(const PhiGrid* g, const PhiVBC* vbc, float* const v[3], const float* p, const float* accessible, void* stream);
 int phicuda_cg_poisson_masked_f32(const PhiGrid* g, const PhiVBC* vbc, const float* rhs, float* x, const float* accessible,
                                   const PhiCgParams* prm, PhiCgResult* result, void* workspace, size_t workspace_bytes,
                                   void* stream);

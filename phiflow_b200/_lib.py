@@ -77,6 +77,8 @@ PROTOTYPES = {
                                          C.c_void_p, C.c_size_t, C.c_void_p]),
     'phicuda_make_incompressible_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), F3, C.c_void_p, C.c_void_p, _P(PhiCgParams),
                                                   C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'phicuda_divergence_masked_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), F3, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'phicuda_grad_sub_masked_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), F3, C.c_void_p, C.c_void_p, C.c_void_p]),
     'phicuda_mul_faces_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), F3, F3, C.c_void_p]),
     'phicuda_cg_poisson_masked_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), C.c_void_p, C.c_void_p, C.c_void_p, _P(PhiCgParams),
                                                 C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -87,6 +89,8 @@ PROTOTYPES = {
     'phicuda_comm_destroy': (C.c_int, [C.c_void_p]),
     'phicuda_cg_poisson_dist_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), C.c_void_p, C.c_void_p, _P(PhiCgParams), C.c_void_p,
                                               C.c_void_p, C.c_void_p]),
+    'phicuda_cg_poisson_dist_masked_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), C.c_void_p, C.c_void_p, C.c_void_p, _P(PhiCgParams), C.c_void_p,
+                                                     C.c_void_p, C.c_void_p]),
     'phicuda_plume_scratch_bytes': (C.c_size_t, [_P(PhiGrid)]),
     'phicuda_plume_step_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), _P(PhiBC), F3, C.c_void_p, C.c_void_p, C.c_void_p,
                                          _P(PhiPlumeParams), _P(PhiCgParams), C.c_void_p, C.c_void_p, C.c_void_p,

@@ -206,17 +206,25 @@ def laplace_axpy(dom: Domain, bc, x, coeff: float, out=None):
     return out
 
 
-def divergence(dom: Domain, vbc, v: List[torch.Tensor], out=None):
-    """field.divergence of a staggered grid (phi/field/_field_math.py:617-626)."""
+def divergence(dom: Domain, vbc, v: List[torch.Tensor], out=None, accessible=None):
+    """field.divergence of a staggered grid (phi/field/_field_math.py:617-626); accessible: div *= active mask (fluid.py:138-141)."""
     require_cuda()
     out = dom.alloc_centered() if out is None else out
+    if accessible is not None:
+        _lib.check(_lib.load().phicuda_divergence_masked_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(v, dom.foff),
+                                                            _ptr(accessible, dom.coff), _ptr(out, dom.coff), _stream()))
+        return out
     _lib.check(_lib.load().phicuda_divergence_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(v, dom.foff), _ptr(out, dom.coff), _stream()))
     return out
 
 
-def grad_sub(dom: Domain, vbc, v: List[torch.Tensor], p: torch.Tensor):
-    """v -= spatial_gradient(p, at='face') in place (phi/physics/fluid.py:158-161)."""
+def grad_sub(dom: Domain, vbc, v: List[torch.Tensor], p: torch.Tensor, accessible=None):
+    """v -= spatial_gradient(p, at='face') in place (phi/physics/fluid.py:158-161); accessible: gradient *= hard_bcs (:159-160)."""
     require_cuda()
+    if accessible is not None:
+        _lib.check(_lib.load().phicuda_grad_sub_masked_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(v, dom.foff), _ptr(p, dom.coff),
+                                                          _ptr(accessible, dom.coff), _stream()))
+        return v
     _lib.check(_lib.load().phicuda_grad_sub_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(v, dom.foff), _ptr(p, dom.coff), _stream()))
     return v
 

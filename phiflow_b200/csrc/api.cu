@@ -322,11 +322,29 @@ static int accessible_field(const PhiGrid* g, const PhiVBC* vbc, DField* af)
     PhiBC abc; memset(&abc, 0, sizeof(abc));
     for (int a = 0; a < g->dim; ++a) {
         const uint8_t kl = vbc->comp[a].lo[a], kh = vbc->comp[a].hi[a];
-        abc.lo[a] = kl == PHI_BC_PERIODIC ? PHI_BC_PERIODIC : PHI_BC_CONST; abc.clo[a] = kl == PHI_BC_ZERO_GRADIENT ? 1.f : 0.f;
-        abc.hi[a] = kh == PHI_BC_PERIODIC ? PHI_BC_PERIODIC : PHI_BC_CONST; abc.chi[a] = kh == PHI_BC_ZERO_GRADIENT ? 1.f : 0.f;
-        if (kl == PHI_BC_HALO || kh == PHI_BC_HALO) { phi_set_error("obstacles are not supported on z-slabs yet"); return PHI_ERR_UNSUPPORTED; }
+        // z-slab sides: the mask of the neighbouring slab sits in the halo planes (static: exchanged once by the caller)
+        abc.lo[a] = (kl == PHI_BC_PERIODIC || kl == PHI_BC_HALO) ? kl : PHI_BC_CONST; abc.clo[a] = kl == PHI_BC_ZERO_GRADIENT ? 1.f : 0.f;
+        abc.hi[a] = (kh == PHI_BC_PERIODIC || kh == PHI_BC_HALO) ? kh : PHI_BC_CONST; abc.chi[a] = kh == PHI_BC_ZERO_GRADIENT ? 1.f : 0.f;
     }
     return phi_make_centered(g, &abc, af);
+}
+
+int phicuda_divergence_masked_f32(const PhiGrid* g, const PhiVBC* vbc, const float* const v[3], const float* accessible, float* div, void* stream)
+{
+    DGrid dg; DVec dv; DField cf; PhiBC none; memset(&none, 0, sizeof(none));
+    CHECK(phi_make_dgrid(g, &dg)); CHECK(make_vec(g, vbc, v, &dv)); CHECK(phi_make_centered(g, &none, &cf));
+    if (!div || !accessible) { phi_set_error("divergence_masked: NULL argument"); return PHI_ERR_INVALID; }
+    return cuda_fail(phi_launch_divergence(dg, dv, cf, div, accessible, (cudaStream_t)stream), "divergence_masked");
+}
+
+int phicuda_grad_sub_masked_f32(const PhiGrid* g, const PhiVBC* vbc, float* const v[3], const float* p, const float* accessible, void* stream)
+{
+    DGrid dg; DVec dv; DVecOut out; PhiBC pbc; DField pf, af;
+    CHECK(phi_make_dgrid(g, &dg)); CHECK(make_vec(g, vbc, v, &dv));
+    CHECK(phi_pressure_bc(vbc, g->dim, &pbc)); CHECK(phi_make_centered(g, &pbc, &pf)); CHECK(accessible_field(g, vbc, &af));
+    if (!p || !accessible) { phi_set_error("grad_sub_masked: NULL argument"); return PHI_ERR_INVALID; }
+    for (int c = 0; c < 3; ++c) out.p[c] = c < g->dim ? v[c] : nullptr;
+    return cuda_fail(phi_launch_grad_sub(dg, dv, out, pf, p, &af, accessible, (cudaStream_t)stream), "grad_sub_masked");
 }
 
 int phicuda_mul_faces_f32(const PhiGrid* g, const PhiVBC* vbc, float* const v[3], const float* const mask[3], void* stream)

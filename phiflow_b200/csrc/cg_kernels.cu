@@ -317,7 +317,7 @@ int phi_launch_cg(const CgLaunch& l, cudaStream_t s)
     const bool adaptive = l.prm.method == PHI_SOLVER_CG_ADAPTIVE;
     if (l.prm.method != PHI_SOLVER_CG && !adaptive) { phi_set_error("cg: unknown solver method %d", l.prm.method); return PHI_ERR_INVALID; }
     if (adaptive && l.prm.matrix_offset != 0.f) { phi_set_error("cg: CG-adaptive does not take a matrix_offset"); return PHI_ERR_UNSUPPORTED; }
-    if (phi_ring_enabled() && !mask) {
+    if (phi_ring_enabled()) {        // obstacles included: the mask is staged as an extra haloed array of the ring
         const int e = phi_launch_cg_ring(l, nullptr, s);
         if (e != -100) return e;
     }

@@ -78,8 +78,26 @@ int phicuda_comm_destroy(PhiComm* c)
     return 0;
 }
 
+static int cg_dist(const PhiGrid* g, const PhiVBC* vbc, const float* rhs, float* x, const float* accessible,
+                   const PhiCgParams* prm, PhiCgResult* result, PhiComm* c, void* stream);
+
 int phicuda_cg_poisson_dist_f32(const PhiGrid* g, const PhiVBC* vbc, const float* rhs, float* x,
                                 const PhiCgParams* prm, PhiCgResult* result, PhiComm* c, void* stream)
+{
+    return cg_dist(g, vbc, rhs, x, nullptr, prm, result, c, stream);
+}
+
+int phicuda_cg_poisson_dist_masked_f32(const PhiGrid* g, const PhiVBC* vbc, const float* rhs, float* x, const float* accessible,
+                                       const PhiCgParams* prm, PhiCgResult* result, PhiComm* c, void* stream)
+{
+    if (!accessible) { phi_set_error("cg_dist_masked: accessible is NULL"); return PHI_ERR_INVALID; }
+    return cg_dist(g, vbc, rhs, x, accessible, prm, result, c, stream);
+}
+
+}  // extern "C"
+
+static int cg_dist(const PhiGrid* g, const PhiVBC* vbc, const float* rhs, float* x, const float* accessible,
+                   const PhiCgParams* prm, PhiCgResult* result, PhiComm* c, void* stream)
 {
     if (!c || !g || !vbc || !rhs || !x || !prm || !result) { phi_set_error("cg_dist: NULL argument"); return PHI_ERR_INVALID; }
     if (memcmp(g, &c->grid, sizeof(PhiGrid)) != 0) { phi_set_error("cg_dist: grid differs from the one the communicator was created for"); return PHI_ERR_INVALID; }
@@ -87,7 +105,7 @@ int phicuda_cg_poisson_dist_f32(const PhiGrid* g, const PhiVBC* vbc, const float
     int e = phi_make_dgrid(g, &l.g); if (e) return e;
     e = phi_pressure_bc(vbc, g->dim, &pbc); if (e) return e;
     e = phi_make_centered(g, &pbc, &l.pf); if (e) return e;
-    l.rhs = rhs; l.x = x; l.prm = *prm; l.result = result;
+    l.rhs = rhs; l.x = x; l.prm = *prm; l.result = result; l.acc = accessible;
     l.workspace = c->local + c->off_ws; l.workspace_bytes = c->ws_bytes;
     CommDev cm;
     memset(&cm, 0, sizeof(cm));
@@ -109,5 +127,3 @@ int phicuda_cg_poisson_dist_f32(const PhiGrid* g, const PhiVBC* vbc, const float
     if (e == -100) { phi_set_error("cg_dist: the grid does not fit the TMA ring kernel"); return PHI_ERR_UNSUPPORTED; }
     return e;
 }
-
-}  // extern "C"

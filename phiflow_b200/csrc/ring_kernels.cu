@@ -122,9 +122,10 @@ struct ProdUnit {
     int tot_h, tot_e;           // warp totals of active lines
 };
 
+// hactive: bit k set = haloed slot k is fetched (slot 1 idles in the first CG iteration; with obstacles the last slot is the mask)
 template <int DIM>
 __device__ __forceinline__ void prod_unit_setup(ProdUnit& pu, const RingCfg& cfg, const DGrid& g, const DField& pf,
-                                                int NH, int NHslots, int NE, const float* const* hsrc, const float* const* esrc,
+                                                unsigned hactive, int NHslots, int NE, const float* const* hsrc, const float* const* esrc,
                                                 int b, int y0)
 {
     const int lane = threadIdx.x & 31, hrows = cfg.TY + 2;
@@ -141,7 +142,7 @@ __device__ __forceinline__ void prod_unit_setup(ProdUnit& pu, const RingCfg& cfg
         if (r < NHslots * hrows) {
             const int arr = r / hrows, j = r - arr * hrows;
             int yy = y0 - 1 + j; float cv;
-            if (arr < NH && yy <= g.n[1] && phi_resolve(yy, pf, 1, cv)) {
+            if (((hactive >> arr) & 1u) && yy <= g.n[1] && phi_resolve(yy, pf, 1, cv)) {
                 pu.yoff[it] = (long long)b * pf.sb + (long long)yy * pf.sy;
                 pu.base[it] = hsrc[arr];
                 pu.dsto[it] = 4u * (uint32_t)((arr * hrows + j) * cfg.pitch);
@@ -277,14 +278,18 @@ __device__ __forceinline__ void groups_tile(ThreadGroups& tg, const RingCfg& cfg
 
 // ---- consumer: one plane of one tile ---------------------------------------------------------------------------------
 // sm/sc/sp: stages holding planes z-1, z, z+1 (sm/sp unused in 2-D).  Values of the differenced array are h0 (+ beta*h1).
-template <int DIM, int NH, int NE, class Epi>
+// MASK (N4, static obstacles): the last haloed slot of a stage holds the accessible mask; the stencil becomes
+//   q_c = sum_faces min(acc_c, acc_nb) * (v_nb - v_c) / dx^2 for fluid cells, q_c = v_c inside obstacles
+// (fluid.masked_laplace, phi/physics/fluid.py:197-202); constant (Dirichlet) ghost cells count as accessible.
+template <int DIM, int NH, int NE, bool MASK = false, class Epi>
 __device__ __forceinline__ void ring_compute(const RingCfg& cfg, const DGrid& g, const DField& pf, const ThreadGroups& tg,
                                              const float* sm, const float* sc, const float* sp, float beta,
                                              long long plane_off, int z, Epi& epi)
 {
     const int pitch = cfg.pitch;
     const int h1 = (cfg.TY + 2) * pitch;                 // offset of the second haloed array inside a stage
-    const int e0off = NH * (cfg.TY + 2) * pitch;
+    const int aoff = NH * (cfg.TY + 2) * pitch;          // MASK: offset of the accessible mask
+    const int e0off = (NH + (MASK ? 1 : 0)) * (cfg.TY + 2) * pitch;
     const int e1off = e0off + cfg.TY * pitch;
     const float ix2 = g.inv_dx2[0], iy2 = g.inv_dx2[1], iz2 = g.inv_dx2[2];
     const bool zm_const = DIM == 3 && z == 0 && pf.klo[2] == PHI_BC_CONST;
@@ -339,6 +344,41 @@ __device__ __forceinline__ void ring_compute(const RingCfg& cfg, const DGrid& g,
         }
         float4 r4 = make_float4(c.y, c.z, c.w, xr);
         if (nvalid < 4) f4_set(r4, nvalid - 1, xr);
+        if (MASK) {
+            // the mask travels like the values: same staged lines, ghost cells 1 where the value ghost is a constant
+            const float* am = sm + aoff; const float* ac_ = sc + aoff; const float* ap = sp + aoff;
+            const float4 ac = *reinterpret_cast<const float4*>(ac_ + rc);
+            const int row = rc - (tg.eoff[k] - tg.j[k] * pitch);
+            const int nx = g.n[0];
+            float axl = (f & GF_XLO) ? (pf.klo[0] == PHI_BC_PERIODIC ? ac_[row + nx - 1] : (pf.klo[0] == PHI_BC_ZERO_GRADIENT ? ac.x : 1.f)) : ac_[rc - 1];
+            float axr = (f & GF_XHI) ? (pf.khi[0] == PHI_BC_PERIODIC ? ac_[row] : (pf.khi[0] == PHI_BC_ZERO_GRADIENT ? f4_get(ac, nvalid - 1) : 1.f)) : ac_[rc + 4];
+            const float4 al4 = make_float4(axl, ac.x, ac.y, ac.z);
+            float4 ar4 = make_float4(ac.y, ac.z, ac.w, axr);
+            if (nvalid < 4) f4_set(ar4, nvalid - 1, axr);
+            const float4 l4 = make_float4(xl, c.x, c.y, c.z);
+            const float4 aym = (f & GF_YLOC) ? f4_splat(1.f) : *reinterpret_cast<const float4*>(ac_ + rc - pitch);
+            const float4 ayp = (f & GF_YHIC) ? f4_splat(1.f) : *reinterpret_cast<const float4*>(ac_ + rc + pitch);
+            auto term = [](float vn, float vc, float an, float a0) { return fminf(an, a0) * (vn - vc); };
+            q.x = (term(l4.x, c.x, al4.x, ac.x) + term(r4.x, c.x, ar4.x, ac.x)) * ix2 + (term(ym.x, c.x, aym.x, ac.x) + term(yp.x, c.x, ayp.x, ac.x)) * iy2;
+            q.y = (term(l4.y, c.y, al4.y, ac.y) + term(r4.y, c.y, ar4.y, ac.y)) * ix2 + (term(ym.y, c.y, aym.y, ac.y) + term(yp.y, c.y, ayp.y, ac.y)) * iy2;
+            q.z = (term(l4.z, c.z, al4.z, ac.z) + term(r4.z, c.z, ar4.z, ac.z)) * ix2 + (term(ym.z, c.z, aym.z, ac.z) + term(yp.z, c.z, ayp.z, ac.z)) * iy2;
+            q.w = (term(l4.w, c.w, al4.w, ac.w) + term(r4.w, c.w, ar4.w, ac.w)) * ix2 + (term(ym.w, c.w, aym.w, ac.w) + term(yp.w, c.w, ayp.w, ac.w)) * iy2;
+            if (DIM == 3) {
+                const float4 zm = zm_const ? f4_splat(pf.clo[2]) : val4(sm, rc);
+                const float4 zp = zp_const ? f4_splat(pf.chi[2]) : val4(sp, rc);
+                const float4 azm = zm_const ? f4_splat(1.f) : *reinterpret_cast<const float4*>(am + rc);
+                const float4 azp = zp_const ? f4_splat(1.f) : *reinterpret_cast<const float4*>(ap + rc);
+                q.x += (term(zm.x, c.x, azm.x, ac.x) + term(zp.x, c.x, azp.x, ac.x)) * iz2;
+                q.y += (term(zm.y, c.y, azm.y, ac.y) + term(zp.y, c.y, azp.y, ac.y)) * iz2;
+                q.z += (term(zm.z, c.z, azm.z, ac.z) + term(zp.z, c.z, azp.z, ac.z)) * iz2;
+                q.w += (term(zm.w, c.w, azm.w, ac.w) + term(zp.w, c.w, azp.w, ac.w)) * iz2;
+            }
+            if (ac.x == 0.f) q.x = c.x;
+            if (ac.y == 0.f) q.y = c.y;
+            if (ac.z == 0.f) q.z = c.z;
+            if (ac.w == 0.f) q.w = c.w;
+            epi.set_acc(ac);
+        } else {
         q.x = (xl + r4.x - 2.f * c.x) * ix2 + (ym.x + yp.x - 2.f * c.x) * iy2;
         q.y = (c.x + r4.y - 2.f * c.y) * ix2 + (ym.y + yp.y - 2.f * c.y) * iy2;
         q.z = (c.y + r4.z - 2.f * c.z) * ix2 + (ym.z + yp.z - 2.f * c.z) * iy2;
@@ -350,6 +390,7 @@ __device__ __forceinline__ void ring_compute(const RingCfg& cfg, const DGrid& g,
             q.y += (zm.y + zp.y - 2.f * c.y) * iz2;
             q.z += (zm.z + zp.z - 2.f * c.z) * iz2;
             q.w += (zm.w + zp.w - 2.f * c.w) * iz2;
+        }
         }
         float4 e0 = f4_splat(0.f), e1 = f4_splat(0.f), e2 = f4_splat(0.f);
         if (NE >= 1) e0 = *reinterpret_cast<const float4*>(sc + e0off + tg.eoff[k]);
@@ -424,19 +465,20 @@ __device__ __forceinline__ void ring_compute_fast(const RingCfg& cfg, const DGri
     zs.have = MARCH && DIM == 3 && G <= 2;
 }
 
-template <bool GENERIC, int DIM, int NH, int NE, bool MARCH, class Epi>
+template <bool GENERIC, int DIM, int NH, int NE, bool MARCH, bool MASK = false, class Epi>
 __device__ __forceinline__ void ring_compute_any(const RingCfg& cfg, const DGrid& g, const DField& pf, const ThreadGroups& tg,
                                                  bool fast, const float* sm, const float* sc, const float* sp, float beta,
                                                  long long plane_off, int z, Epi& epi, ZMarch& zs)
 {
     if (cfg.dbg & 4) return;
+    if (MASK) { zs.have = false; ring_compute<DIM, NH, NE, true>(cfg, g, pf, tg, sm, sc, sp, beta, plane_off, z, epi); return; }
     if (!GENERIC || fast) {
         if (cfg.groups == 4) { ring_compute_fast<DIM, NH, NE, 4, MARCH>(cfg, g, tg, sm, sc, sp, beta, plane_off, epi, zs); return; }
         if (cfg.groups == 2) { ring_compute_fast<DIM, NH, NE, 2, MARCH>(cfg, g, tg, sm, sc, sp, beta, plane_off, epi, zs); return; }
         if (cfg.groups == 1) { ring_compute_fast<DIM, NH, NE, 1, MARCH>(cfg, g, tg, sm, sc, sp, beta, plane_off, epi, zs); return; }
     }
     zs.have = false;
-    if (GENERIC) ring_compute<DIM, NH, NE>(cfg, g, pf, tg, sm, sc, sp, beta, plane_off, z, epi);
+    if (GENERIC) ring_compute<DIM, NH, NE, false>(cfg, g, pf, tg, sm, sc, sp, beta, plane_off, z, epi);
 }
 
 // ---- one unit: producer streams its planes, consumers march through them --------------------------------------------------
@@ -454,7 +496,7 @@ __device__ __forceinline__ RingUnit ring_unit(const RingCfg& cfg, const DGrid& g
 }
 
 // consumers, 3-D: march through the planes of one unit.  G > 0: every plane takes the branch-free path with G groups.
-template <bool GENERIC, int NH, int NE, bool MARCH, int G, class Epi>
+template <bool GENERIC, int NH, int NE, bool MARCH, int G, bool MASK = false, class Epi>
 __device__ __forceinline__ void ring_consume_planes(Ring& rg, const RingCfg& cfg, const DGrid& g, const DField& pf, const ThreadGroups& tg,
                                                     bool tile_fast, float beta, long long plane_off, const RingUnit& u, Epi& epi)
 {
@@ -473,8 +515,8 @@ __device__ __forceinline__ void ring_consume_planes(Ring& rg, const RingCfg& cfg
                                                                      beta, plane_off, epi, zs);
         } else {
             const bool fast = tile_fast && !(z == 0 && pf.klo[2] == PHI_BC_CONST) && !(z == g.n[2] - 1 && pf.khi[2] == PHI_BC_CONST);
-            ring_compute_any<GENERIC, 3, NH, NE, MARCH>(cfg, g, pf, tg, fast, ring_ptr(rg, cfg, a), ring_ptr(rg, cfg, bq), ring_ptr(rg, cfg, c2),
-                                                        beta, plane_off, z, epi, zs);
+            ring_compute_any<GENERIC, 3, NH, NE, MARCH, MASK>(cfg, g, pf, tg, fast, ring_ptr(rg, cfg, a), ring_ptr(rg, cfg, bq), ring_ptr(rg, cfg, c2),
+                                                              beta, plane_off, z, epi, zs);
         }
         ring_release(rg, a);
         a = bq; bq = c2; c2.next(cfg.R);
@@ -484,7 +526,8 @@ __device__ __forceinline__ void ring_consume_planes(Ring& rg, const RingCfg& cfg
     rg.pos = c2;
 }
 
-template <bool GENERIC, int DIM, int NH, int NE, bool MARCH = true, class Epi>
+// MASK: hsrc[NH] is the accessible mask; it occupies the haloed slot after the NH value arrays.
+template <bool GENERIC, int DIM, int NH, int NE, bool MARCH = true, bool MASK = false, class Epi>
 __device__ __forceinline__ void ring_process_unit(Ring& rg, const RingCfg& cfg, const DGrid& g, const DField& pf,
                                                   ThreadGroups& tg,
                                                   const float* const* hsrc, const float* const* esrc, float beta,
@@ -494,7 +537,7 @@ __device__ __forceinline__ void ring_process_unit(Ring& rg, const RingCfg& cfg, 
     if (producer) {
         const int nh = (NH == 2 && beta == 0.f) ? 1 : NH;          // first CG iteration: d' = r, old direction not read
         ProdUnit pu;
-        prod_unit_setup<DIM>(pu, cfg, g, pf, nh, NH, NE, hsrc, esrc, u.b, u.y0);
+        prod_unit_setup<DIM>(pu, cfg, g, pf, ((1u << nh) - 1u) | (MASK ? (1u << NH) : 0u), NH + (MASK ? 1 : 0), NE, hsrc, esrc, u.b, u.y0);
         if (DIM == 3) {
             const int nz = u.z1 - u.z0;
             for (int p = 0; p < nz + 2; ++p)
@@ -505,8 +548,8 @@ __device__ __forceinline__ void ring_process_unit(Ring& rg, const RingCfg& cfg, 
         return;
     }
     const int ny = g.n[1];
-    const bool tile_fast = !GENERIC || tg.fast_ok && u.y0 + cfg.TY <= ny
-                           && !(u.y0 == 0 && pf.klo[1] == PHI_BC_CONST) && !(u.y0 + cfg.TY == ny && pf.khi[1] == PHI_BC_CONST);
+    const bool tile_fast = !MASK && (!GENERIC || tg.fast_ok && u.y0 + cfg.TY <= ny
+                           && !(u.y0 == 0 && pf.klo[1] == PHI_BC_CONST) && !(u.y0 + cfg.TY == ny && pf.khi[1] == PHI_BC_CONST));
     if (GENERIC) groups_tile(tg, cfg, g, pf, u.y0);      // also needed on fast tiles: planes with constant z ghosts take the slow path
     long long plane_off = (long long)u.b * pf.sb + (long long)u.y0 * pf.sy + (DIM == 3 ? (long long)u.z0 * pf.sz : 0);
     if (DIM == 3) {
@@ -514,14 +557,14 @@ __device__ __forceinline__ void ring_process_unit(Ring& rg, const RingCfg& cfg, 
         if (!GENERIC && cfg.groups == 2) ring_consume_planes<GENERIC, NH, NE, MARCH, 2>(rg, cfg, g, pf, tg, tile_fast, beta, plane_off, u, epi);
         else if (!GENERIC && cfg.groups == 4) ring_consume_planes<GENERIC, NH, NE, MARCH, 4>(rg, cfg, g, pf, tg, tile_fast, beta, plane_off, u, epi);
         else if (!GENERIC) ring_consume_planes<GENERIC, NH, NE, MARCH, 1>(rg, cfg, g, pf, tg, tile_fast, beta, plane_off, u, epi);
-        else ring_consume_planes<GENERIC, NH, NE, MARCH, 0>(rg, cfg, g, pf, tg, tile_fast, beta, plane_off, u, epi);
+        else ring_consume_planes<GENERIC, NH, NE, MARCH, 0, MASK>(rg, cfg, g, pf, tg, tile_fast, beta, plane_off, u, epi);
     } else {
         const SlotIt a = rg.pos;
         ring_wait_full(rg, a);
         const float* sc = ring_ptr(rg, cfg, a);
         epi.set_plane(-1, 0);
         ZMarch zs; zs.have = false;
-        ring_compute_any<GENERIC, DIM, NH, NE, MARCH>(cfg, g, pf, tg, tile_fast, sc, sc, sc, beta, plane_off, 0, epi, zs);
+        ring_compute_any<GENERIC, DIM, NH, NE, MARCH, MASK>(cfg, g, pf, tg, tile_fast, sc, sc, sc, beta, plane_off, 0, epi, zs);
         ring_release(rg, a);
         rg.pos.next(cfg.R);
     }
@@ -557,6 +600,7 @@ template <bool AXPY>
 struct REpiLaplace {
     float* y; float coeff;
     __device__ __forceinline__ void set_plane(int, int) {}
+    __device__ __forceinline__ void set_acc(const float4&) {}
     __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid, const float4&, const float4&, const float4&)
     {
         float4 o = q;
@@ -569,12 +613,14 @@ struct REpiLaplace {
 template <class PH>
 struct REpiResidual0 {          // e0 = rhs
     float* r; float mean, offs; float acc0, acc1; PH ph; bool tol_from_y;   // CG-adaptive: tolerance relative to |y|^2
+    float4 am = make_float4(1.f, 1.f, 1.f, 1.f);      // obstacles: balanced rhs = y - mean * accessible (fluid.py:205-209)
     __device__ __forceinline__ void set_plane(int z, int nz) { ph.set_plane(z, nz); }
+    __device__ __forceinline__ void set_acc(const float4& a) { am = a; }
     __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid, const float4& y, const float4&, const float4&)
     {
-        float4 rt = make_float4((y.x - mean) - q.x, (y.y - mean) - q.y, (y.z - mean) - q.z, (y.w - mean) - q.w);
+        float4 rt = make_float4((y.x - mean * am.x) - q.x, (y.y - mean * am.y) - q.y, (y.z - mean * am.z) - q.z, (y.w - mean * am.w) - q.w);
         float4 rr = make_float4(rt.x - offs, rt.y - offs, rt.z - offs, rt.w - offs);
-        if (tol_from_y) rt = make_float4(y.x - mean, y.y - mean, y.z - mean, y.w - mean);
+        if (tol_from_y) rt = make_float4(y.x - mean * am.x, y.y - mean * am.y, y.z - mean * am.z, y.w - mean * am.w);
         if (nvalid == 4) {
             *reinterpret_cast<float4*>(r + off) = rr;
             if (ph.zf) ph.put4(off, rr);
@@ -586,6 +632,7 @@ struct REpiResidual0 {          // e0 = rhs
 
 template <class PH>
 struct REpiPassA {
+    __device__ __forceinline__ void set_acc(const float4&) {}
     float* dnew; float acc0, acc1; PH ph;
     __device__ __forceinline__ void set_plane(int z, int nz) { ph.set_plane(z, nz); }
     __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid, const float4&, const float4&, const float4&)
@@ -602,6 +649,7 @@ struct REpiPassA {
 // CG-adaptive pass A: the second sum is d'.r (e0 = r, element-wise), _linalg.py:113
 template <class PH>
 struct REpiPassAAdapt {
+    __device__ __forceinline__ void set_acc(const float4&) {}
     float* dnew; float acc0, acc1; PH ph;
     __device__ __forceinline__ void set_plane(int z, int nz) { ph.set_plane(z, nz); }
     __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid, const float4& re, const float4&, const float4&)
@@ -618,7 +666,8 @@ struct REpiPassAAdapt {
 // The solution update is applied every second iteration only: x_{k+1} = x_{k-1} + alpha_{k-1} d_{k-1} + alpha_k d_k needs
 // the previous direction (still intact in the other d buffer) but saves one read+write of x: 30 instead of 32 B/cell/it.
 template <class PH, bool RQ = false>      // RQ (CG-adaptive): the second sum is r_new . q (_linalg.py:119)
-struct REpiPassBr {             // odd iterations: e0 = r; x is left alone
+struct REpiPassBr {
+    __device__ __forceinline__ void set_acc(const float4&) {}             // odd iterations: e0 = r; x is left alone
     float* r; float alpha, offs; float acc0, acc1; PH ph;
     __device__ __forceinline__ void set_plane(int z, int nz) { ph.set_plane(z, nz); }
     __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid, const float4& re, const float4&, const float4&)
@@ -635,7 +684,8 @@ struct REpiPassBr {             // odd iterations: e0 = r; x is left alone
 };
 
 template <class PH, bool RQ = false>
-struct REpiPassB {              // even iterations: e0 = x, e1 = r, e2 = previous direction
+struct REpiPassB {
+    __device__ __forceinline__ void set_acc(const float4&) {}              // even iterations: e0 = x, e1 = r, e2 = previous direction
     float* x; float* r; float alpha, aprev, offs; float acc0, acc1; PH ph;
     __device__ __forceinline__ void set_plane(int z, int nz) { ph.set_plane(z, nz); }
     __device__ __forceinline__ void operator()(long long off, const float4& c, const float4& q, int nvalid, const float4& xe, const float4& re, const float4& dp)
@@ -747,7 +797,8 @@ __device__ __forceinline__ void ring_unit_cells(const RingCfg& cfg, const DGrid&
         }
 }
 
-template <int DIM, bool GENERIC, bool DIST, bool ADAPT>
+// MASK (N4): static obstacles - a.acc is the accessible mask, staged as an extra haloed array (always the GENERIC consumer).
+template <int DIM, bool GENERIC, bool DIST, bool ADAPT, bool MASK = false>
 __global__ void __launch_bounds__(RING_THREADS, 1)
 k_cg_ring(CgRingArgs A)
 {
@@ -813,23 +864,23 @@ k_cg_ring(CgRingArgs A)
     if (a.prm.balance_rhs || coffs != 0.f) {
         sweep(nullptr, [&](const RingUnit& u, float& acc0, float& acc1) {
             ring_unit_cells<DIM>(cfg, g, a.pf, tg, u, [&](long long off, int nvalid) {
-                for (int j = 0; j < nvalid; ++j) { acc0 += a.rhs[off + j]; acc1 += a.x[off + j]; }
+                for (int j = 0; j < nvalid; ++j) { acc0 += a.rhs[off + j]; acc1 += MASK ? a.acc[off + j] : a.x[off + j]; }
             });
         });
         barrier_and_reduce(nullptr);
         for (int b = threadIdx.x; b < batch; b += blockDim.x) {
-            sh.mean[b] = a.prm.balance_rhs ? (float)(sh.sum0[b] / cells) : 0.f;
-            sh.offs[b] = coffs * (float)sh.sum1[b];
+            if (MASK) { sh.mean[b] = (a.prm.balance_rhs && sh.sum1[b] > 0.0) ? (float)(sh.sum0[b] / sh.sum1[b]) : 0.f; sh.offs[b] = 0.f; }
+            else { sh.mean[b] = a.prm.balance_rhs ? (float)(sh.sum0[b] / cells) : 0.f; sh.offs[b] = coffs * (float)sh.sum1[b]; }
         }
         __syncthreads();
     }
 
     {   // r0 = y - (A + c 11^T) x0
-        const float* hsrc[2] = {a.x, nullptr};
+        const float* hsrc[2] = {a.x, MASK ? a.acc : nullptr};
         const float* esrc[2] = {a.rhs, nullptr};
         sweep(nullptr, [&](const RingUnit& u, float& acc0, float& acc1) {
             REpiResidual0<PH> epi{a.r, sh.mean[u.b], sh.offs[u.b], 0.f, 0.f, peer_halo(cm.lo_r, cm.hi_r), adaptive};
-            ring_process_unit<GENERIC, DIM, 1, 1>(rg, cfg, g, a.pf, tg, hsrc, esrc, 0.f, u, epi);
+            ring_process_unit<GENERIC, DIM, 1, 1, true, MASK>(rg, cfg, g, a.pf, tg, hsrc, esrc, 0.f, u, epi);
             acc0 += epi.acc0; acc1 += epi.acc1;
         });
     }
@@ -856,11 +907,11 @@ k_cg_ring(CgRingArgs A)
     bool x_pending = false;      // all running entries are at the same iteration, so one flag describes them all
     while (*sh.any_cont && comm_ok) {
         if (cfg.dbg & 1) {} else if constexpr (!ADAPT) {   // pass A
-            const float* hsrc[2] = {a.r, dold};
+            const float* hsrc[3] = {a.r, dold, MASK ? a.acc : nullptr};
             const float* esrc[2] = {nullptr, nullptr};
             sweep(sh.cont, [&](const RingUnit& u, float& acc0, float& acc1) {
                 REpiPassA<PH> epi{dnew, 0.f, 0.f, peer_halo(lo_dnew, hi_dnew)};
-                ring_process_unit<GENERIC, DIM, 2, 0>(rg, cfg, g, a.pf, tg, hsrc, esrc, sh.beta[u.b], u, epi);
+                ring_process_unit<GENERIC, DIM, 2, 0, true, MASK>(rg, cfg, g, a.pf, tg, hsrc, esrc, sh.beta[u.b], u, epi);
                 acc0 += epi.acc0; acc1 += epi.acc1;
             });
         } else {                                    // pass A of CG-adaptive: additionally d'.r (r once more, element-wise)
@@ -890,7 +941,7 @@ k_cg_ring(CgRingArgs A)
         }
         __syncthreads();
         if (cfg.dbg & 2) {} else if (!x_pending) {   // pass B, odd iteration: r only, the x update is deferred
-            const float* hsrc[2] = {dnew, nullptr};
+            const float* hsrc[2] = {dnew, MASK ? a.acc : nullptr};
             const float* esrc[3] = {a.r, nullptr, nullptr};
             sweep(sh.cont, [&](const RingUnit& u, float& acc0, float& acc1) {
                 if constexpr (ADAPT) {
@@ -899,12 +950,12 @@ k_cg_ring(CgRingArgs A)
                     acc0 += epi.acc0; acc1 += epi.acc1;
                 } else {
                     REpiPassBr<PH> epi{a.r, sh.alpha[u.b], sh.offs[u.b], 0.f, 0.f, peer_halo(cm.lo_r, cm.hi_r)};
-                    ring_process_unit<GENERIC, DIM, 1, 1>(rg, cfg, g, a.pf, tg, hsrc, esrc, 0.f, u, epi);
+                    ring_process_unit<GENERIC, DIM, 1, 1, true, MASK>(rg, cfg, g, a.pf, tg, hsrc, esrc, 0.f, u, epi);
                     acc0 += epi.acc0;
                 }
             });
         } else {            // pass B, even iteration: x += alpha_prev d_prev + alpha d
-            const float* hsrc[2] = {dnew, nullptr};
+            const float* hsrc[2] = {dnew, MASK ? a.acc : nullptr};
             const float* esrc[3] = {a.x, a.r, dold};
             sweep(sh.cont, [&](const RingUnit& u, float& acc0, float& acc1) {
                 if constexpr (ADAPT) {
@@ -913,7 +964,7 @@ k_cg_ring(CgRingArgs A)
                     acc0 += epi.acc0; acc1 += epi.acc1;
                 } else {
                     REpiPassB<PH> epi{a.x, a.r, sh.alpha[u.b], sh.aprev[u.b], sh.offs[u.b], 0.f, 0.f, peer_halo(cm.lo_r, cm.hi_r)};
-                    ring_process_unit<GENERIC, DIM, 1, 3>(rg, cfg, g, a.pf, tg, hsrc, esrc, 0.f, u, epi);
+                    ring_process_unit<GENERIC, DIM, 1, 3, true, MASK>(rg, cfg, g, a.pf, tg, hsrc, esrc, 0.f, u, epi);
                     acc0 += epi.acc0;
                 }
             });
@@ -961,15 +1012,15 @@ k_cg_ring(CgRingArgs A)
     if (a.prm.project_mean) {
         sweep(nullptr, [&](const RingUnit& u, float& acc0, float& acc1) {
             ring_unit_cells<DIM>(cfg, g, a.pf, tg, u, [&](long long off, int nvalid) {
-                for (int j = 0; j < nvalid; ++j) acc0 += a.x[off + j];
+                for (int j = 0; j < nvalid; ++j) { if (MASK) { acc0 += a.x[off + j] * a.acc[off + j]; acc1 += a.acc[off + j]; } else acc0 += a.x[off + j]; }
             });
         });
         barrier_and_reduce(nullptr);
         for (int unit = blockIdx.x; unit < cfg.total_units; unit += gridDim.x) {
             const RingUnit u = ring_unit<DIM>(cfg, g, unit);
-            const float m = (float)(sh.sum0[u.b] / cells);
+            const float m = MASK ? (sh.sum1[u.b] > 0.0 ? (float)(sh.sum0[u.b] / sh.sum1[u.b]) : 0.f) : (float)(sh.sum0[u.b] / cells);
             ring_unit_cells<DIM>(cfg, g, a.pf, tg, u, [&](long long off, int nvalid) {
-                for (int j = 0; j < nvalid; ++j) a.x[off + j] -= m;
+                for (int j = 0; j < nvalid; ++j) a.x[off + j] -= MASK ? m * a.acc[off + j] : m;
             });
         }
     }
@@ -1055,10 +1106,10 @@ static bool ring_all_fast(const DGrid& g, const DField& f, const RingCfg& c)
     return c.groups == 1 || c.groups == 2 || c.groups == 4;
 }
 
-static void note_ring_launch(int kernel, const RingCfg& c, bool generic, bool dist, bool adaptive, int grid)
+static void note_ring_launch(int kernel, const RingCfg& c, bool generic, bool dist, bool adaptive, int grid, bool masked = false)
 {
     PhiLaunchInfo li; memset(&li, 0, sizeof(li));
-    li.kernel = kernel; li.generic = generic; li.dist = dist; li.adaptive = adaptive;
+    li.kernel = kernel; li.generic = generic; li.dist = dist; li.adaptive = adaptive; li.masked = masked;
     li.TY = c.TY; li.stages = c.R; li.ZC = c.ZC; li.nzc = c.nzc; li.groups = c.groups; li.total_units = c.total_units; li.grid_ctas = grid;
     phi_note_launch(li);
 }
@@ -1099,23 +1150,29 @@ int phi_launch_laplace_ring(const DGrid& g, const DField& f, const float* x, flo
 int phi_launch_cg_ring(const CgLaunch& l, const CommDev* cm, cudaStream_t s)
 {
     const DGrid& g = l.g;
-    if (g.batch > CG_MAX_BATCH || l.acc) return -100;
+    if (g.batch > CG_MAX_BATCH) return -100;
+    const bool mask = l.acc != nullptr;
+    if (mask && (l.prm.method == PHI_SOLVER_CG_ADAPTIVE || l.prm.matrix_offset != 0.f)) return -100;
     CgRingArgs A;
     const int cgs = (int)((cg_smem_bytes(g.batch) + 127) / 128 * 128);
     const int sms = sm_count();
-    if (!ring_config(g, 4, 2, cgs, g.dim == 3 ? 4 : 2, RING_MAX_STAGES, sms, &A.cfg)) return -100;
+    // lines staged per stage: pass B (even) = 1 haloed + 3 element-wise arrays = 4 TY + 2; with the obstacle mask as an extra
+    // haloed array 5 TY + 4 (pass A: 3 haloed = 3 TY + 6)
+    if (!ring_config(g, mask ? 5 : 4, mask ? 6 : 2, cgs, g.dim == 3 ? (mask ? 3 : 4) : 2, RING_MAX_STAGES, sms, &A.cfg)) return -100;
     const int threads = RING_THREADS;
     A.ring_smem_offset = cgs;
     const size_t smem = (size_t)cgs + 128 + (size_t)A.cfg.R * A.cfg.stage_floats * 4;
     int per_sm = 0;
     cudaError_t e;
-    const bool generic = !ring_all_fast(g, l.pf, A.cfg);
+    const bool generic = mask || !ring_all_fast(g, l.pf, A.cfg);
     const bool dist = cm && cm->n > 1;
     const bool adapt = l.prm.method == PHI_SOLVER_CG_ADAPTIVE;
 #define CG_RING_FN2(D, GEN, DI) (adapt ? (const void*)k_cg_ring<D, GEN, DI, true> : (const void*)k_cg_ring<D, GEN, DI, false>)
 #define CG_RING_FN(D, GEN) (dist ? CG_RING_FN2(D, GEN, true) : CG_RING_FN2(D, GEN, false))
     const void* fn = g.dim == 3 ? (generic ? CG_RING_FN(3, true) : CG_RING_FN(3, false))
                                 : (generic ? CG_RING_FN(2, true) : CG_RING_FN(2, false));
+    if (mask) fn = g.dim == 3 ? (dist ? (const void*)k_cg_ring<3, true, true, false, true> : (const void*)k_cg_ring<3, true, false, false, true>)
+                              : (dist ? (const void*)k_cg_ring<2, true, true, false, true> : (const void*)k_cg_ring<2, true, false, false, true>);
 #undef CG_RING_FN
 #undef CG_RING_FN2
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1129,7 +1186,7 @@ int phi_launch_cg_ring(const CgLaunch& l, const CommDev* cm, cudaStream_t s)
     unsigned char* ws = (unsigned char*)l.workspace;
     CgArgs& a = A.a;
     a.g = g; a.pf = l.pf; a.um = UnitMap();
-    a.rhs = l.rhs; a.x = l.x; a.acc = nullptr;
+    a.rhs = l.rhs; a.x = l.x; a.acc = l.acc;
     const size_t hoff = (size_t)g.halo * g.cext[0] * g.cext[1];       // pointers address the first owned plane
     a.r = (float*)ws + hoff; a.d0 = (float*)(ws + arr) + hoff; a.d1 = (float*)(ws + 2 * arr) + hoff;
     a.partials = (double*)(ws + 3 * arr);
@@ -1138,6 +1195,6 @@ int phi_launch_cg_ring(const CgLaunch& l, const CommDev* cm, cudaStream_t s)
     void* args[] = {&A};
     e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, smem, s);
     if (e != cudaSuccess) { phi_set_error("cg ring: cooperative launch failed: %s", cudaGetErrorString(e)); return (int)e; }
-    note_ring_launch(PHI_KERNEL_CG_RING, A.cfg, generic, dist, adapt, grid);
+    note_ring_launch(PHI_KERNEL_CG_RING, A.cfg, generic, dist, adapt, grid, mask);
     return 0;
 }

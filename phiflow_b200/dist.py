@@ -153,15 +153,36 @@ class Slab:
             self._result = torch.zeros(6, dtype=torch.int32, device=self.dom.device)
         return self._comm
 
-    def cg_poisson(self, rhs: torch.Tensor, x: torch.Tensor, prm):
-        """CG over all slabs; x (with valid halo planes) is updated in place.  Single rank: the ordinary solve."""
+    def cg_poisson(self, rhs: torch.Tensor, x: torch.Tensor, prm, accessible: torch.Tensor = None):
+        """CG over all slabs; x (with valid halo planes) is updated in place.  Single rank: the ordinary solve.
+        accessible: static obstacle mask with valid halo planes (N4)."""
         if self.world == 1:
+            assert accessible is None, "single-rank masked solves go through ops.make_incompressible(accessible=...)"
             return ops.cg_poisson(self.dom, self.vbc, rhs, x, prm)
         comm = self._communicator()
         dom = self.dom
+        if accessible is not None:
+            _lib.check(_lib.load().phicuda_cg_poisson_dist_masked_f32(C.byref(dom.grid), C.byref(ops.make_vbc(self.vbc, 3)), ops._ptr(rhs, dom.coff),
+                                                                      ops._ptr(x, dom.coff), ops._ptr(accessible, dom.coff), C.byref(prm),
+                                                                      ops._ptr(self._result), comm, ops._stream()))
+            return x
         _lib.check(_lib.load().phicuda_cg_poisson_dist_f32(C.byref(dom.grid), C.byref(ops.make_vbc(self.vbc, 3)), ops._ptr(rhs, dom.coff),
                                                            ops._ptr(x, dom.coff), C.byref(prm), ops._ptr(self._result), comm, ops._stream()))
         return x
+
+    def make_incompressible(self, v: List[torch.Tensor], p: torch.Tensor, div: torch.Tensor, prm, accessible: torch.Tensor = None,
+                            vmask: List[torch.Tensor] = None):
+        """fluid.make_incompressible on z-slabs (phi/physics/fluid.py:94-162), optionally with static obstacles (N4): the caller
+        passes the accessible mask and the face factors of apply_boundary_conditions with valid halo planes."""
+        if accessible is not None and vmask is not None:
+            ops.mul_faces(self.dom, self.vbc, v, vmask)
+        self.exchange(v, 1)
+        ops.divergence(self.dom, self.vbc, v, out=div, accessible=accessible)
+        self.exchange([p], 1)
+        self.cg_poisson(div, p, prm, accessible=accessible)
+        self.exchange([p], 1)
+        ops.grad_sub(self.dom, self.vbc, v, p, accessible=accessible)
+        return v, p
 
     def results(self):
         if self.world == 1:

@@ -521,6 +521,8 @@ def test_make_incompressible_with_obstacle(vname, big):
     dacc = dom.centered_from_numpy(acc)
     prm = ops.cg_params(vbc, rtol=1e-5, atol=1e-6)
     dv, dp = ops.make_incompressible(dom, vbc, dv, None, prm, accessible=dacc)
+    launch = ops.last_launch_info()          # obstacles run on the TMA ring (mask staged as an extra haloed array), not the marching kernel
+    assert launch['kernel'] == 3 and launch['masked'] == 1 and launch['generic'] == 1, launch
     info = ops.read_results(dom)
     assert info['converged'][0] == 1 and info['diverged'][0] == 0
     v_ref, p_ref, inf = O.make_incompressible_obstacles(v, vbc, res, dx, acc, vmask, rtol=1e-5, atol=1e-6)

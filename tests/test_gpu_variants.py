@@ -168,6 +168,39 @@ def test_make_incompressible_fast_variant(res, vname):
         np.testing.assert_allclose(got[c], v_ref[c], rtol=0, atol=1e-4 * max(np.abs(v[c]).max(), 1e-3))
 
 
+@pytest.mark.parametrize('vname', ['periodic', 'wall', 'per_wall'])
+def test_masked_ring_cg_multi_unit(vname):
+    """N4 on the TMA ring at a size with several units per persistent CTA: obstacles (one touching the boundary, one in the
+    interior) against the oracle's masked projection (phi/physics/fluid.py:121-162, 197-202)."""
+    vbc = {'periodic': PER3, 'wall': WALL3, 'per_wall': PER_WALL3}[vname]
+    res = (256, 32, 24)
+    dx = tuple(50.0 / r for r in res)
+    rng = np.random.default_rng(36)
+    acc = np.ones(res, np.float32)
+    acc[60:110, 8:20, 5:14] = 0
+    acc[0:12, 0:6, 18:24] = 0
+    hard = O.hard_bcs_faces(acc, vbc)
+    v = [(0.1 * rng.standard_normal(s)).astype(np.float32) for s in O.staggered_shapes(res, vbc)]
+    vmask = [h.copy() for h in hard]
+    with ring_nzc(6):
+        dom = ops.Domain(res, dx, 1, vbc=vbc)
+        dv = dom.faces_from_numpy(v, vbc)
+        ops.mul_faces(dom, vbc, dv, dom.faces_from_numpy(vmask, vbc))
+        prm = ops.cg_params(vbc, rtol=1e-5, atol=1e-6, max_iter=3000)
+        dv, dp = ops.make_incompressible(dom, vbc, dv, None, prm, accessible=dom.centered_from_numpy(acc))
+        li = ops.last_launch_info()
+    assert li['kernel'] == _lib.KERNEL_CG_RING and li['masked'] == 1 and li['total_units'] > li['grid_ctas'], li
+    info = ops.read_results(dom)
+    assert info['converged'][0] == 1 and info['diverged'][0] == 0
+    v_ref, p_ref, inf = O.make_incompressible_obstacles(v, vbc, res, dx, acc, vmask, rtol=1e-5, atol=1e-6, max_iter=3000)
+    assert abs(int(info['iterations'][0]) - inf['iterations']) <= max(3, inf['iterations'] // 8), (info['iterations'], inf['iterations'])
+    got = dom.faces_to_numpy(dv, vbc)
+    for c in range(3):
+        np.testing.assert_allclose(got[c], v_ref[c], rtol=0, atol=2e-4 * max(np.abs(v[c]).max(), 1e-3))
+    p = dom.centered_to_numpy(dp)
+    assert np.abs(p[acc == 0]).max() == 0.0
+
+
 def _plume_parity(res, steps, expect_fast):
     """The step bench.py times (phicuda_plume_step_f32 through ops.plume_step: periodic velocity, open smoke, inflow sphere,
     buoyancy along z, CG rtol 1e-3 warm start) against the oracle restatement of the notebook step."""

@@ -165,6 +165,64 @@ def run_oracle_case(name, disp_cells, steps, rtol=1e-5, start_halo=3):
     return bool(flag.item())
 
 
+def run_obstacle_case(name, rtol=1e-5):
+    """N4 on z-slabs: make_incompressible with a static obstacle that straddles a slab face, against the single-GPU masked
+    projection (the masked TMA-ring CG on both sides; same iterates up to the order of the dot-product reductions)."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    res = (128, 24, 8 * world)
+    nx, ny, nz = res
+    dx = tuple(50.0 / r for r in res)
+    vbc = ((0.0, 0.0), ('periodic', 'periodic'), ('periodic', 'periodic'))
+    rng = np.random.default_rng(17)
+    acc = np.ones((nz, ny, nx), np.float32)
+    acc[nz // 2 - 3:nz // 2 + 2, 6:14, 40:70] = 0           # crosses the interface between two slabs
+    acc[:2, 2:5, 5:20] = 0                                   # touches the periodic wrap in z
+    v0 = [(0.1 * rng.standard_normal((1, nz, ny, nx + 4))).astype(np.float32) for _ in range(3)]
+    prm = ops.cg_params(vbc, rtol=rtol, atol=1e-7, max_iter=3000)
+    slab = Slab(res, dx, vbc, halo=2, device=dev)
+    d, H, nzl, z0 = slab.dom, slab.halo, slab.nz, slab.z0
+    v = d.alloc_faces()
+    for c in range(3):
+        v[c][:, H:H + nzl, :, :d.fext[0]] = torch.from_numpy(v0[c][:, z0:z0 + nzl, :, :d.fext[0]]).to(dev)
+    a = d.alloc_centered()
+    a[0, H:H + nzl, :, :nx] = torch.from_numpy(acc[z0:z0 + nzl]).to(dev)
+    slab.exchange([a], H)
+    p, div = d.alloc_centered(), d.alloc_centered()
+    slab.make_incompressible(v, p, div, prm, accessible=a)
+    it_dist = int(slab.results()['iterations'][0])
+    info = ops.last_launch_info()
+    own = lambda t: t[:, H:H + nzl].contiguous()
+    def gather(t):
+        parts = [torch.empty_like(own(t)) for _ in range(world)]
+        dist.all_gather(parts, own(t))
+        return torch.cat(parts, dim=1)
+    p_all = gather(p)
+    v_all = [gather(t) for t in v]
+    ok = True
+    if rank == 0:
+        dom = ops.Domain(res, dx, 1, vbc=vbc, device=dev)
+        vs = dom.alloc_faces()
+        for c in range(3):
+            vs[c][:, :, :, :dom.fext[0]] = torch.from_numpy(v0[c][:, :, :, :dom.fext[0]]).to(dev)
+        accs = dom.alloc_centered()
+        accs[0, :, :, :nx] = torch.from_numpy(acc).to(dev)
+        vs, ps = ops.make_incompressible(dom, vbc, vs, None, prm, accessible=accs)
+        r = ops.read_results(dom)
+        sinfo = ops.last_launch_info()
+        dp = float((p_all - ps).abs().max()); pm = float(ps.abs().max())
+        dv = [float((v_all[c] - vs[c]).abs().max()) for c in range(3)]
+        vmax = max(float(t.abs().max()) for t in vs)
+        print(f"[{name}] world={world} masked ring: dist kernel masked={info['masked']} dist={info['dist']}, single masked={sinfo['masked']} kernel={sinfo['kernel']} | "
+              f"iters dist={it_dist} single={int(r['iterations'][0])} max|p diff|={dp:.3e} (max {pm:.3e}) max|v diff|={dv} (vmax {vmax:.3e})", flush=True)
+        ok = info['masked'] == 1 and sinfo['masked'] == 1 and abs(it_dist - int(r['iterations'][0])) <= 3 and dp <= 50 * rtol * max(pm, 1e-6) \
+            and all(x <= 50 * rtol * vmax for x in dv) and int(r['converged'][0]) == 1
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    slab.close()
+    return bool(flag.item())
+
+
 def main():
     dist.init_process_group('nccl')
     torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
@@ -176,6 +234,7 @@ def main():
     ok &= run_case('periodic', per, zg, (64, 48, 16 * world), 3, 1e-4)
     ok &= run_case('mixed-z-wall-open', mixed, zg, (128, 24, 8 * world), 2, 1e-4)
     ok &= run_oracle_case('cfl-halo-vs-oracle', 6.4, 3)
+    ok &= run_obstacle_case('obstacle-across-slabs')
     if dist.get_rank() == 0:
         print('DIST_CHECK', 'PASS' if ok else 'FAIL', flush=True)
     dist.destroy_process_group()
