@@ -1050,7 +1050,7 @@ static bool ring_config(const DGrid& g, int lines_a, int lines_b, int reserve_by
     // measured on B200 (512^3): TY=4 beats TY=8 for both laplace (6.12 vs 5.85 TB/s) and CG (5.18 vs 5.10 TB/s): smaller
     // stages -> deeper ring; the extra y-halo lines are served by L2
     int ty = g.dim == 3 ? 4 : 16;
-    if (const char* e = getenv("PHICUDA_RING_TY")) { const int v = atoi(e); if (v >= 1 && v <= ty) ty = v; }     // tuning knob
+    if (const char* e = getenv("PHICUDA_RING_TY")) { const int v = atoi(e); if (v >= 1 && v <= 32) ty = v; }     // tuning knob
     for (;; ty /= 2) {
         if (ty < 1) return false;
         if (ty * c.nx4 > RING_G * consumers) continue;                    // <= RING_G groups per thread

@@ -19,6 +19,7 @@ import torch
 
 from . import _ops as ops
 from . import field_io
+from . import scene as _scene
 
 __all__ = ['Box', 'Sphere', 'CenteredGrid', 'StaggeredGrid', 'extrapolation', 'ZERO', 'ONE', 'PERIODIC', 'ZERO_GRADIENT',
            'BOUNDARY', 'combine_sides', 'Solve', 'SolveTape', 'NotConverged', 'Diverged', 'ConvergenceException', 'field',
@@ -536,6 +537,26 @@ field = SimpleNamespace(divergence=divergence, laplace=laplace, spatial_gradient
 # ----------------------------------------------------------------------------------------------------------------------
 # advect  (phi/physics/advect.py)
 # ----------------------------------------------------------------------------------------------------------------------
+class Scene(_scene.Scene):
+    """phi.field.Scene for this package's grids (phi/field/_scene.py:52-426): trajectories as sim_xxxxxx/<name>_<frame>.npz."""
+
+    def __init__(self, path, writer=None, reader=None):
+        super().__init__(path, writer or write, reader or read)
+
+    @staticmethod
+    def create(parent_directory, name='sim', copy_calling_script=False):
+        s = _scene.Scene.create(parent_directory, name, copy_calling_script)
+        return Scene(s.path)
+
+    @staticmethod
+    def at(directory, id=None):
+        return Scene(_scene.Scene.at(directory, id).path)
+
+    @staticmethod
+    def list(parent_directory, name='sim'):
+        return tuple(Scene(s.path) for s in _scene.Scene.list(parent_directory, name))
+
+
 def _check_velocity(fld, velocity):
     _require(isinstance(velocity, StaggeredGrid), "advection by a non-staggered velocity")
     _require(fld.res == velocity.res and fld.lower == velocity.lower and fld.upper == velocity.upper, "advection across different grids")

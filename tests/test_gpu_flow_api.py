@@ -169,3 +169,29 @@ def test_make_incompressible_with_obstacles():
     assert np.abs(div[fluid_cells]).max() < 1e-4
     assert np.abs(vy).max() > 1e-2 and np.abs(vx).max() > 1e-3
     assert np.abs(pressure.numpy()[~fluid_cells]).max() == 0.0
+
+
+def test_scene_trajectory_roundtrip(tmp_path):
+    """Scene.create / write / read (phi/field/_scene.py:107-153, 354-426): a short smoke trajectory on disk, read back bit-exact."""
+    bounds = Box(x=(0, 100), y=(0, 100))
+    smoke = CenteredGrid(Sphere(x=50, y=20, radius=8), ZERO_GRADIENT, bounds, x=24, y=20)
+    velocity = StaggeredGrid(0, ZERO, bounds, x=24, y=20)
+    scene = Scene.create(str(tmp_path), copy_calling_script=False)
+    scene.put_properties(dt=1.0, solver='CG')
+    frames = {}
+    for frame in range(3):
+        velocity = advect.semi_lagrangian(velocity, velocity, 1.0) + resample(smoke * (0, 0.5), to=velocity)
+        velocity, _ = fluid.make_incompressible(velocity, (), Solve('CG', 1e-4, 1e-6))
+        smoke = advect.mac_cormack(smoke, velocity, 1.0)
+        scene.write({'smoke': smoke, 'velocity': velocity}, frame=frame)
+        frames[frame] = (smoke.numpy().copy(), [c.copy() for c in velocity.numpy()])
+    assert scene.fieldnames == ('smoke', 'velocity') and scene.frames == (0, 1, 2) and scene.complete_frames == (0, 1, 2)
+    again = Scene.at(scene.path)
+    assert again.properties == {'dt': 1.0, 'solver': 'CG'}
+    for frame, (s_ref, v_ref) in frames.items():
+        s, v = again.read('smoke', 'velocity', frame=frame)
+        assert isinstance(s, CenteredGrid) and isinstance(v, StaggeredGrid)
+        np.testing.assert_array_equal(s.numpy(), s_ref)
+        for a, b in zip(v.numpy(), v_ref):
+            np.testing.assert_array_equal(a, b)
+        assert v.boundary == velocity.boundary and s.boundary == smoke.boundary

@@ -135,6 +135,31 @@ def test_advect_centered(vname, sname):
     assert bad.mean() < 0.01, f"{bad.sum()} mismatching cells"
 
 
+@pytest.mark.parametrize('name', sorted(ALL_S))
+def test_grid_sample(name):
+    """phicuda_grid_sample_f32 = math.grid_sample at caller-provided coordinates (PhiML/phiml/math/_ops.py:936-1015), the
+    Backend.grid_sample entry of the reference-side plugin; oracle.grid_sample is pinned against vendored-phiml fixtures.
+    Includes the reference's known answers (PhiML/tests/commit/math/test__ops.py:232-245)."""
+    bc = ALL_S[name]
+    d = len(bc)
+    rng = np.random.default_rng(12)
+    res = (23, 14) if d == 2 else (13, 9, 7)
+    batch, npts = 2, 4000
+    dom = ops.Domain(res, (1.0,) * d, batch)
+    grid = rng.standard_normal((batch,) + res).astype(np.float32)
+    # points inside, on cell boundaries, and up to 3 cells outside on every side
+    coords = (rng.uniform(-3.0, 1.0, (batch, npts, d)) + rng.uniform(0, 1, (batch, npts, d)) * (np.array(res) + 2.0)).astype(np.float32)
+    coords[:, :50] = np.round(coords[:, :50])
+    out = ops.grid_sample(dom, bc, dom.centered_from_numpy(grid), torch.from_numpy(coords).cuda()).cpu().numpy()
+    ref = np.stack([O.grid_sample(grid[b], coords[b], bc) for b in range(batch)])
+    np.testing.assert_allclose(out, ref, rtol=0, atol=1e-5 * np.abs(grid).max())
+    if name == 'zero':
+        dom1 = ops.Domain((3, 2), (1.0, 1.0), 1)                      # test__ops.py:232-238: grid = x + y, x in (1, 2, 3), y in (0, 3)
+        g = dom1.centered_from_numpy(np.array([[1.0, 4.0], [2.0, 5.0], [3.0, 6.0]], np.float32))
+        pts = torch.tensor([[[0.0, 0.0], [0.5, 0.0], [0.0, 0.5], [-2.0, -1.0]]], dtype=torch.float32).cuda()
+        np.testing.assert_allclose(ops.grid_sample(dom1, bc, g, pts).cpu().numpy()[0], [1.0, 1.5, 2.5, 0.0], atol=1e-6)
+
+
 @pytest.mark.parametrize('vname', sorted(ALL_V))
 def test_advect_staggered_self(vname):
     vbc = ALL_V[vname]

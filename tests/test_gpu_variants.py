@@ -173,16 +173,16 @@ def test_masked_ring_cg_multi_unit(vname):
     """N4 on the TMA ring at a size with several units per persistent CTA: obstacles (one touching the boundary, one in the
     interior) against the oracle's masked projection (phi/physics/fluid.py:121-162, 197-202)."""
     vbc = {'periodic': PER3, 'wall': WALL3, 'per_wall': PER_WALL3}[vname]
-    res = (256, 32, 24)
+    res = (256, 64, 48)
     dx = tuple(50.0 / r for r in res)
     rng = np.random.default_rng(36)
     acc = np.ones(res, np.float32)
-    acc[60:110, 8:20, 5:14] = 0
-    acc[0:12, 0:6, 18:24] = 0
+    acc[60:110, 18:40, 5:30] = 0
+    acc[0:12, 0:9, 40:48] = 0
     hard = O.hard_bcs_faces(acc, vbc)
     v = [(0.1 * rng.standard_normal(s)).astype(np.float32) for s in O.staggered_shapes(res, vbc)]
     vmask = [h.copy() for h in hard]
-    with ring_nzc(6):
+    with ring_nzc(12):
         dom = ops.Domain(res, dx, 1, vbc=vbc)
         dv = dom.faces_from_numpy(v, vbc)
         ops.mul_faces(dom, vbc, dv, dom.faces_from_numpy(vmask, vbc))
