@@ -752,15 +752,59 @@ def hard_bcs_faces(accessible: np.ndarray, vbc) -> List[np.ndarray]:
     return out
 
 
+DENSE_MASKED_MATRIX_LIMIT = 3000     # cells; above this the column-by-column builder (n x n dense, O(n^2) memory) is replaced by the assembly below
+
+
+def masked_poisson_matrix_sparse(res, dx, vbc, accessible: np.ndarray) -> sp.csr_matrix:
+    """The same operator assembled face by face in O(n): every face between two cells carries the flux
+    min(acc_lower, acc_upper) * (p_upper - p_lower) / dx^2 (hard_bcs = field.stagger(accessible, minimum), fluid.py:134, 197-202);
+    open sides (pressure Dirichlet 0) see an accessible ghost cell with p = 0, walls (pressure Neumann) no flux, periodic sides
+    the wrapped neighbour; obstacle cells are identity rows.  tests/test_oracle_golden.py checks it against the column-by-column
+    builder (which is pinned against the phiml-traced matrix) for every boundary kind."""
+    d = len(res)
+    n = int(np.prod(res))
+    pbc = pressure_bc(vbc)
+    acc = accessible.astype(F32)
+    idx = np.arange(n).reshape(res)
+    rows, cols, vals = [], [], []
+
+    def face(i_l, i_u, w):
+        rows.extend([i_l, i_l, i_u, i_u]); cols.extend([i_l, i_u, i_u, i_l]); vals.extend([-w, w, -w, w])
+
+    for ax in range(d):
+        inv = F32(1) / (F32(dx[ax]) * F32(dx[ax]))
+        lo, hi = pbc[ax]
+        lower = [slice(None)] * d; upper = [slice(None)] * d
+        lower[ax], upper[ax] = slice(0, -1), slice(1, None)
+        if res[ax] > 1:
+            face(idx[tuple(lower)].ravel(), idx[tuple(upper)].ravel(), (np.minimum(acc[tuple(lower)], acc[tuple(upper)]) * inv).ravel())
+        first = [slice(None)] * d; last = [slice(None)] * d
+        first[ax], last[ax] = 0, res[ax] - 1
+        if lo == PERIODIC:
+            face(idx[tuple(last)].ravel(), idx[tuple(first)].ravel(), (np.minimum(acc[tuple(last)], acc[tuple(first)]) * inv).ravel())
+        else:
+            for side, sel in ((lo, first), (hi, last)):
+                if is_const(side):                              # Dirichlet 0 behind an accessible ghost cell: -acc_i * p_i / dx^2
+                    i = idx[tuple(sel)].ravel()
+                    rows.append(i); cols.append(i); vals.append((-acc[tuple(sel)] * inv).ravel())
+    A = sp.coo_matrix((np.concatenate(vals).astype(np.float64), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n)).tocsr()
+    A = A + sp.diags((acc.ravel() == 0).astype(np.float64))
+    A = A.astype(F32)
+    A.sum_duplicates(); A.sort_indices()
+    return A
+
+
 def masked_poisson_matrix(res, dx, vbc, accessible: np.ndarray) -> sp.csr_matrix:
     """Matrix of fluid.masked_laplace with obstacles (fluid.py:197-202): div(hard_bcs * grad p) on active cells,
     identity on inactive ones (`where(active, div, pressure)`).  Built column-block-wise from the oracle's own
     gradient / divergence so that it follows the same restated glue (validated against a phiml-traced matrix)."""
     d = len(res)
     pbc = pressure_bc(vbc)
+    n = int(np.prod(res))
+    if n > DENSE_MASKED_MATRIX_LIMIT:
+        return masked_poisson_matrix_sparse(res, dx, vbc, accessible)
     vbc0 = tuple(tuple(0.0 if is_const(s) else s for s in ax) for ax in vbc)      # remove_constant_offset
     hard = hard_bcs_faces(accessible, vbc)
-    n = int(np.prod(res))
     cols = []
     eye = np.eye(n, dtype=F32)
     for j in range(n):

@@ -40,6 +40,10 @@ struct RingCfg {
     int hint;                  // 1: element-wise lines are fetched with an L2 evict-first policy
     int merge;                 // 1: lines that are contiguous in memory travel in one bulk copy
     int dbg;                   // profiling only (PHICUDA_RING_DEBUG): 1 skip CG pass A, 2 skip pass B, 4 consumers skip the arithmetic
+    // "tail split" decomposition of the CG kernel (3-D, batch 1, fewer y tiles than persistent CTAs): CTA c < nyt marches tile c
+    // over planes [0, Zm); the remaining CTAs share the tails [Zm, nz) of all tiles, split_t tiles each.  Keeps every SM busy
+    // when the tile count does not divide the CTA count (128 tiles on 148 SMs for 512-wide slabs).
+    int split, Zm, split_t;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
@@ -495,6 +499,27 @@ __device__ __forceinline__ RingUnit ring_unit(const RingCfg& cfg, const DGrid& g
     return u;
 }
 
+// k-th unit of this CTA; false when it has no more
+template <int DIM>
+__device__ __forceinline__ bool ring_next_unit(const RingCfg& cfg, const DGrid& g, int k, RingUnit& u)
+{
+    if (!cfg.split) {
+        const int unit = blockIdx.x + k * gridDim.x;
+        if (unit >= cfg.total_units) return false;
+        u = ring_unit<DIM>(cfg, g, unit);
+        return true;
+    }
+    if ((int)blockIdx.x < cfg.nyt) {
+        if (k > 0) return false;
+        u.b = 0; u.y0 = blockIdx.x * cfg.TY; u.z0 = 0; u.z1 = cfg.Zm;
+        return true;
+    }
+    const int t = ((int)blockIdx.x - cfg.nyt) * cfg.split_t + k;
+    if (k >= cfg.split_t || t >= cfg.nyt) return false;
+    u.b = 0; u.y0 = t * cfg.TY; u.z0 = cfg.Zm; u.z1 = g.n[2];
+    return true;
+}
+
 // consumers, 3-D: march through the planes of one unit.  G > 0: every plane takes the branch-free path with G groups.
 template <bool GENERIC, int NH, int NE, bool MARCH, int G, bool MASK = false, class Epi>
 __device__ __forceinline__ void ring_consume_planes(Ring& rg, const RingCfg& cfg, const DGrid& g, const DField& pf, const ThreadGroups& tg,
@@ -819,9 +844,9 @@ k_cg_ring(CgRingArgs A)
     groups_init(tg, cfg, g, a.pf);
 
     auto sweep = [&](const unsigned char* active, auto&& body) {
-        int cur_b = -1; float acc0 = 0.f, acc1 = 0.f;
-        for (int unit = blockIdx.x; unit < cfg.total_units; unit += gridDim.x) {
-            const RingUnit u = ring_unit<DIM>(cfg, g, unit);
+        int cur_b = cfg.split ? 0 : -1; float acc0 = 0.f, acc1 = 0.f;      // split mode: every CTA reports for the one batch entry
+        RingUnit u;
+        for (int k = 0; ring_next_unit<DIM>(cfg, g, k, u); ++k) {
             if (active && !active[u.b]) continue;
             if (u.b != cur_b) {
                 if (cur_b >= 0) flush_partials(sh, a.partials, region, batch, cur_b, acc0, acc1);
@@ -839,7 +864,7 @@ k_cg_ring(CgRingArgs A)
         if (cm.n > 1) __threadfence_system();      // halo planes stored into the neighbours' memory
         grid.sync();
         fence_proxy_async();
-        reduce_partials(sh, a.partials, region, batch, cfg.units_per_batch, active);
+        reduce_partials(sh, a.partials, region, batch, cfg.split ? (int)gridDim.x : cfg.units_per_batch, active);
         region ^= 1;
         if (cm.n > 1) {
             comm_ok = comm_allreduce(cm, sh, batch, ++seq) && comm_ok;
@@ -995,8 +1020,8 @@ k_cg_ring(CgRingArgs A)
     }
 
     // entries that stopped after an odd number of iterations still owe x their last step; odd iterations write d1
-    for (int unit = blockIdx.x; unit < cfg.total_units; unit += gridDim.x) {
-        const RingUnit u = ring_unit<DIM>(cfg, g, unit);
+    RingUnit u;
+    for (int k = 0; ring_next_unit<DIM>(cfg, g, k, u); ++k) {
         if (!(sh.iters[u.b] & 1)) continue;
         const float al = sh.alpha[u.b];
         ring_unit_cells<DIM>(cfg, g, a.pf, tg, u, [&](long long off, int nvalid) {
@@ -1016,8 +1041,7 @@ k_cg_ring(CgRingArgs A)
             });
         });
         barrier_and_reduce(nullptr);
-        for (int unit = blockIdx.x; unit < cfg.total_units; unit += gridDim.x) {
-            const RingUnit u = ring_unit<DIM>(cfg, g, unit);
+        for (int k = 0; ring_next_unit<DIM>(cfg, g, k, u); ++k) {
             const float m = MASK ? (sh.sum1[u.b] > 0.0 ? (float)(sh.sum0[u.b] / sh.sum1[u.b]) : 0.f) : (float)(sh.sum0[u.b] / cells);
             ring_unit_cells<DIM>(cfg, g, a.pf, tg, u, [&](long long off, int nvalid) {
                 for (int j = 0; j < nvalid; ++j) a.x[off + j] -= MASK ? m * a.acc[off + j] : m;
@@ -1044,6 +1068,7 @@ static bool ring_config(const DGrid& g, int lines_a, int lines_b, int reserve_by
                         int target_units, RingCfg* out, int consumers = RING_CONSUMERS)
 {
     RingCfg c;
+    c.split = 0; c.Zm = 0; c.split_t = 0;
     c.consumers = consumers;
     c.pitch = g.cext[0]; c.nx4 = g.cext[0] / 4;
     const int row_bytes = c.pitch * 4;
@@ -1179,7 +1204,28 @@ int phi_launch_cg_ring(const CgLaunch& l, const CommDev* cm, cudaStream_t s)
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem);
     if (e != cudaSuccess || per_sm < 1) return -100;
     int grid = sms * per_sm;
-    if (grid > A.cfg.total_units) grid = A.cfg.total_units;
+    // tail split (see RingCfg): compare the planes the busiest CTA stages per pass, default decomposition vs split
+    A.cfg.split = 0; A.cfg.Zm = 0; A.cfg.split_t = 0;
+    {
+        const char* e = getenv("PHICUDA_RING_SPLIT");                       // tuning knob: 0 = never, 1 = whenever possible
+        const int force = e ? atoi(e) : -1;
+        const int nyt = A.cfg.nyt, nz = g.n[2];
+        if (g.dim == 3 && g.batch == 1 && force != 0 && grid <= CG_MAX_GRID && nyt < grid && nz >= 8) {
+            const int spare = grid - nyt, T = (nyt + spare - 1) / spare;
+            int best_zm = 0; long long best = 1ll << 60;
+            for (int zm = 4; zm <= nz - 1; ++zm) {
+                const long long cost = (long long)(zm + 2) > (long long)T * (nz - zm + 2) ? (zm + 2) : (long long)T * (nz - zm + 2);
+                if (cost < best) { best = cost; best_zm = zm; }
+            }
+            const long long rounds = ((long long)A.cfg.total_units + grid - 1) / grid;
+            const long long dflt = rounds * (A.cfg.ZC + 2);
+            if (best_zm > 0 && (force == 1 || best * 100 < dflt * 97)) {
+                A.cfg.split = 1; A.cfg.Zm = best_zm; A.cfg.split_t = T;
+                A.cfg.nzc = 2; A.cfg.ZC = best_zm; A.cfg.units_per_batch = A.cfg.total_units = 2 * nyt;
+            }
+        }
+    }
+    if (!A.cfg.split && grid > A.cfg.total_units) grid = A.cfg.total_units;
     if (grid > CG_MAX_GRID) grid = CG_MAX_GRID;
     const size_t pf_sb = (size_t)g.cext[0] * g.cext[1] * g.cext[2];
     const size_t arr = ((size_t)pf_sb * g.batch * sizeof(float) + 255) / 256 * 256;

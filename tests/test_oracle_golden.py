@@ -299,3 +299,27 @@ def test_obstacle_masks_and_masked_laplace_match_phiml(name):
     np.testing.assert_allclose(A.dot(p.ravel()).reshape(acc.shape), ref, rtol=0, atol=4e-6 * np.abs(ref).max())
     if f'obst/{name}/matrix' in GOLD.files:
         np.testing.assert_allclose(A.toarray(), GOLD[f'obst/{name}/matrix'], rtol=1e-6, atol=1e-6)
+
+
+def test_masked_matrix_sparse_assembly_matches_column_builder():
+    """oracle.masked_poisson_matrix switches to an O(n) face-by-face assembly above DENSE_MASKED_MATRIX_LIMIT cells (the
+    column-by-column builder needs an n x n dense array: 2.5 TB at 256 x 64 x 48).  Both must give the same matrix for every
+    boundary kind and random obstacle masks; the column builder is the one pinned against the phiml-traced matrix."""
+    import itertools
+    rng = np.random.default_rng(0)
+    kinds = [('periodic', 'periodic'), (0.0, 0.0), ('zg', 'zg'), (0.0, 'zg'), ('zg', 0.0)]
+    old = O.DENSE_MASKED_MATRIX_LIMIT
+    try:
+        O.DENSE_MASKED_MATRIX_LIMIT = 10 ** 9
+        for d, res in ((2, (7, 6)), (3, (5, 4, 6))):
+            for combo in itertools.product(kinds, repeat=d):
+                acc = (rng.uniform(size=res) > 0.25).astype(np.float32)
+                dx = tuple(rng.uniform(0.3, 2.0, d))
+                a = O.masked_poisson_matrix(res, dx, tuple(combo), acc).toarray()
+                b = O.masked_poisson_matrix_sparse(res, dx, tuple(combo), acc).toarray()
+                assert np.abs(a - b).max() <= 2e-6 * np.abs(a).max(), combo
+    finally:
+        O.DENSE_MASKED_MATRIX_LIMIT = old
+    # and the switch itself: a grid above the limit never allocates the dense array
+    big = O.masked_poisson_matrix((64, 32, 16), (1.0, 1.0, 1.0), ((0.0, 0.0),) * 3, np.ones((64, 32, 16), np.float32))
+    assert big.shape == (32768, 32768) and big.nnz < 8 * 32768
