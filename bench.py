@@ -498,7 +498,7 @@ def main():
     ap.add_argument('--size', type=int, default=512)
     ap.add_argument('--batch', type=int, default=64, help='c5: batch entries per GPU')
     ap.add_argument('--cpu-size', type=int, default=96, dest='cpu_size')
-    ap.add_argument('--cpu-sizes', default=None, dest='cpu_sizes', help='comma-separated sample grids of the CPU baseline (default: 96,128; reference arm 96,128,256)')
+    ap.add_argument('--cpu-sizes', default=None, dest='cpu_sizes', help='comma-separated sample grids of the CPU baseline (default: 96,128; add 256 for a ~6-minute third sample)')
     ap.add_argument('--no-cpu', action='store_true', dest='no_cpu')
     ap.add_argument('--halo', type=int, default=16, help='z-slab halo planes allocated per side (N>1); grows on demand')
     args = ap.parse_args()
@@ -506,7 +506,7 @@ def main():
         args.size = 256
     if args.impl == 'reference':
         if args.cpu_sizes is None and args.cpu_size == 96:
-            args.cpu_sizes = '96,128,256'
+            args.cpu_sizes = '96,128'          # 256^3 takes ~5 min per step: opt in with --cpu-sizes 96,128,256 (recorded: profiles/r2_cpu_samples.json)
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
     if args.cpu_sizes is None and args.cpu_size == 96:

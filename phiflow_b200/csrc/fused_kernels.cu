@@ -30,11 +30,12 @@
 // halo planes are negative) or a constant ghost line, marked by this sentinel.
 #define FK_CONST_LINE (-(1ll << 62))
 
-// value at index x of a resolved line; x outside the stored range follows the boundary (same resolution order as phi_fetch)
+// value at index x of a resolved line; x outside the stored range follows the boundary (same resolution order as phi_fetch:
+// z, then y, then x - a constant ghost LINE wins over a constant x ghost)
 __device__ __forceinline__ float fk_ldx(const float* __restrict__ a, const RowRef<3>& r, const DField& f, int x)
 {
-    if (x < f.lo[0] || x > f.hi[0]) { float c; if (!phi_resolve(x, f, 0, c)) return c; }
     if (r.off == FK_CONST_LINE) return r.cval;
+    if (x < f.lo[0] || x > f.hi[0]) { float c; if (!phi_resolve(x, f, 0, c)) return c; }
     return __ldg(a + r.off + x);
 }
 
@@ -42,8 +43,8 @@ template <int DIM>
 __device__ __forceinline__ RowRef<3> fk_row(const DGrid& g, const DField& f, int b, int y, int z)
 {
     RowRef<3> r; r.cval = 0.f; r.off = FK_CONST_LINE;
-    if (!phi_resolve(y, f, 1, r.cval)) return r;
     if (DIM == 3) { if (!phi_resolve(z, f, 2, r.cval)) return r; } else z = 0;
+    if (!phi_resolve(y, f, 1, r.cval)) return r;
     r.off = (long long)b * f.sb + (long long)z * f.sz + (long long)y * f.sy;
     return r;
 }

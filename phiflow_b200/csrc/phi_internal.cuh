@@ -64,10 +64,12 @@ __device__ __forceinline__ bool phi_resolve(int& i, const DField& f, int a, floa
 template <int DIM>
 __device__ __forceinline__ float phi_fetch(const float* __restrict__ a, const DGrid& g, const DField& f, int b, int x, int y, int z)
 {
+    // Outside in more than one axis: the reference pads axis by axis (math.pad, _ops.py:791-838), so a corner ghost cell holds what
+    // the axis padded LAST put there - resolve the last axis first.  (Only visible when two axes carry different constants.)
     float c = 0.f;
-    if (!phi_resolve(x, f, 0, c)) return c;
-    if (!phi_resolve(y, f, 1, c)) return c;
     if (DIM == 3) { if (!phi_resolve(z, f, 2, c)) return c; } else z = 0;
+    if (!phi_resolve(y, f, 1, c)) return c;
+    if (!phi_resolve(x, f, 0, c)) return c;
     return __ldg(a + (long long)b * f.sb + (long long)z * f.sz + (long long)y * f.sy + x);
 }
 
@@ -118,8 +120,8 @@ template <int DIM>
 __device__ __forceinline__ RowRef<DIM> phi_row(const DGrid& g, const DField& f, int b, int y, int z)
 {
     RowRef<DIM> r; r.cval = 0.f; r.off = -1;
-    if (!phi_resolve(y, f, 1, r.cval)) return r;
     if (DIM == 3) { if (!phi_resolve(z, f, 2, r.cval)) return r; } else z = 0;
+    if (!phi_resolve(y, f, 1, r.cval)) return r;
     r.off = (long long)b * f.sb + (long long)z * f.sz + (long long)y * f.sy;
     return r;
 }

@@ -1062,6 +1062,8 @@ k_cg_ring(CgRingArgs A)
 
 // ---- host side ------------------------------------------------------------------------------------------------------------
 static const int kSmemBudget = 227 * 1024;
+// cost of starting a unit, in plane loads (512 x 512 x 64, tails of 6 planes x 7 units against one unit of 64: +5 % instead of -9 %)
+#define RING_UNIT_OVERHEAD 2.5
 
 // lines staged per stage = lines_a * TY + lines_b; returns false when the grid lines are too long for a useful ring
 static bool ring_config(const DGrid& g, int lines_a, int lines_b, int reserve_bytes, int min_stages, int max_stages,
@@ -1075,6 +1077,14 @@ static bool ring_config(const DGrid& g, int lines_a, int lines_b, int reserve_by
     // measured on B200 (512^3): TY=4 beats TY=8 for both laplace (6.12 vs 5.85 TB/s) and CG (5.18 vs 5.10 TB/s): smaller
     // stages -> deeper ring; the extra y-halo lines are served by L2
     int ty = g.dim == 3 ? 4 : 16;
+    if (g.dim == 3) {
+        // measured (tools/sweep_ring.py, 256^3): a CTA wants >= 2048 cells per staged plane - TY=4 146 us, TY=8 114 us, TY=16 114 us
+        // per CG iteration, TY=2 538 us; the per-plane mbarrier bookkeeping is amortised over TY * nx cells.  512 -> 4, 256 -> 8, ...
+        const int want = 2048 / (g.cext[0] > 0 ? g.cext[0] : 1);
+        ty = 1;
+        while (ty * 2 <= want && ty < 16) ty *= 2;
+        while (ty > 1 && ty / 2 >= g.n[1]) ty /= 2;
+    }
     if (const char* e = getenv("PHICUDA_RING_TY")) { const int v = atoi(e); if (v >= 1 && v <= 32) ty = v; }     // tuning knob
     for (;; ty /= 2) {
         if (ty < 1) return false;
@@ -1093,9 +1103,9 @@ static bool ring_config(const DGrid& g, int lines_a, int lines_b, int reserve_by
     { const char* e = getenv("PHICUDA_RING_DEBUG"); c.dbg = e ? atoi(e) : 0; }
     if (g.dim == 3) {
         c.nyt = (g.n[1] + c.TY - 1) / c.TY;
-        // z chunking: every unit pays a pipeline refill + two halo planes (~ (ZC+2)/ZC), and the persistent grid of
-        // `ctas` CTAs is only fully busy when the unit count is close to a multiple of it -> maximise
-        //   utilisation(units, ctas) / (1 + 2/ZC)
+        // z chunking: every unit pays two halo planes plus a pipeline start (measured: ~2.5 plane loads, RING_UNIT_OVERHEAD), and
+        // the persistent grid of `ctas` CTAs is only fully busy when the unit count is close to a multiple of it -> maximise
+        //   utilisation(units, ctas) / (1 + (2 + overhead)/ZC)
         const int ctas = target_units;
         double best = -1.0; int best_nzc = 1;
         const int max_nzc = g.n[2] >= 4 ? g.n[2] / 4 : 1;
@@ -1105,7 +1115,7 @@ static bool ring_config(const DGrid& g, int lines_a, int lines_b, int reserve_by
             const long long units = (long long)c.nyt * nzc * g.batch;
             const long long rounds = (units + ctas - 1) / ctas;
             const double util = (double)units / (double)(rounds * ctas);
-            const double score = util / (1.0 + 2.0 / zc);
+            const double score = util / (1.0 + (2.0 + RING_UNIT_OVERHEAD) / zc);
             if (score > best + 1e-9) { best = score; best_nzc = nzc; }
         }
         if (const char* e = getenv("PHICUDA_RING_NZC")) {                     // tuning knob
@@ -1212,14 +1222,15 @@ int phi_launch_cg_ring(const CgLaunch& l, const CommDev* cm, cudaStream_t s)
         const int nyt = A.cfg.nyt, nz = g.n[2];
         if (g.dim == 3 && g.batch == 1 && force != 0 && grid <= CG_MAX_GRID && nyt < grid && nz >= 8) {
             const int spare = grid - nyt, T = (nyt + spare - 1) / spare;
-            int best_zm = 0; long long best = 1ll << 60;
+            int best_zm = 0; double best = 1e30;
             for (int zm = 4; zm <= nz - 1; ++zm) {
-                const long long cost = (long long)(zm + 2) > (long long)T * (nz - zm + 2) ? (zm + 2) : (long long)T * (nz - zm + 2);
+                const double main_c = zm + 2 + RING_UNIT_OVERHEAD, tail_c = T * (nz - zm + 2 + RING_UNIT_OVERHEAD);
+                const double cost = main_c > tail_c ? main_c : tail_c;
                 if (cost < best) { best = cost; best_zm = zm; }
             }
             const long long rounds = ((long long)A.cfg.total_units + grid - 1) / grid;
-            const long long dflt = rounds * (A.cfg.ZC + 2);
-            if (best_zm > 0 && (force == 1 || best * 100 < dflt * 97)) {
+            const double dflt = rounds * (A.cfg.ZC + 2 + RING_UNIT_OVERHEAD);
+            if (best_zm > 0 && (force == 1 || best < dflt * 0.97)) {
                 A.cfg.split = 1; A.cfg.Zm = best_zm; A.cfg.split_t = T;
                 A.cfg.nzc = 2; A.cfg.ZC = best_zm; A.cfg.units_per_batch = A.cfg.total_units = 2 * nyt;
             }

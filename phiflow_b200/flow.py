@@ -21,7 +21,7 @@ from . import _ops as ops
 from . import field_io
 from . import scene as _scene
 
-__all__ = ['Box', 'Sphere', 'CenteredGrid', 'StaggeredGrid', 'extrapolation', 'ZERO', 'ONE', 'PERIODIC', 'ZERO_GRADIENT',
+__all__ = ['Scene', 'Box', 'Sphere', 'CenteredGrid', 'StaggeredGrid', 'extrapolation', 'ZERO', 'ONE', 'PERIODIC', 'ZERO_GRADIENT',
            'BOUNDARY', 'combine_sides', 'Solve', 'SolveTape', 'NotConverged', 'Diverged', 'ConvergenceException', 'field',
            'resample', 'advect', 'diffuse', 'fluid', 'math', 'write', 'read']
 
