@@ -280,7 +280,7 @@ def run_ours(args):
                        "api": "one phicuda_plume_step_f32 call per step (5 kernel launches + 1 device copy)",
                        "cg_iterations_per_step": float(np.mean(iters)), "cg_ms_per_step": float(np.mean(cg_ms)),
                        "non_cg_ms_per_step": float(ms - np.mean(cg_ms)),
-                       "cg_kernel_variant": {k: variant[k] for k in ('kernel', 'generic', 'TY', 'stages', 'ZC', 'nzc', 'groups', 'total_units', 'grid_ctas')},
+                       "cg_kernel_variant": {k: variant[k] for k in ('kernel', 'generic', 'TY', 'stages', 'ZC', 'nzc', 'groups', 'total_units', 'grid_ctas', 'split')},
                        "l2": f"inputs ({4 * n ** 3 / 2 ** 20:.0f} MiB per array) exceed L2, no flush"},
             "clocks": clocks, "gpu_launches": sim.launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "kernel": "k_cg_ring<3,GENERIC=false,DIST=false> (persistent CG solve)", "achieved": cg_gbs, "peak": peak, "unit": "GB/s",

@@ -122,6 +122,7 @@ typedef struct PhiLaunchInfo {
     int32_t groups;        /* float4 groups per consumer thread and plane */
     int32_t total_units;   /* units of the whole launch */
     int32_t grid_ctas;     /* CTAs launched (units per CTA = ceil(total_units / grid_ctas)) */
+    int32_t split;         /* CG ring: 1 = tail-split decomposition (CTA c < tiles marches planes [0, ZC), the rest share the tails) */
 } PhiLaunchInfo;
 int phicuda_last_launch_info(PhiLaunchInfo* out);
 

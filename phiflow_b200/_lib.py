@@ -40,7 +40,7 @@ class PhiCgResult(C.Structure):
 
 class PhiLaunchInfo(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ('kernel', 'generic', 'dist', 'adaptive', 'masked', 'TY', 'stages', 'ZC', 'nzc', 'groups',
-                                         'total_units', 'grid_ctas')]
+                                         'total_units', 'grid_ctas', 'split')]
 
 
 KERNEL_NONE, KERNEL_LAPLACE_RING, KERNEL_LAPLACE_MARCH, KERNEL_CG_RING, KERNEL_CG_MARCH, KERNEL_STENCIL_RING = range(6)

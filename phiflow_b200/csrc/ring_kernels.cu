@@ -1145,7 +1145,7 @@ static void note_ring_launch(int kernel, const RingCfg& c, bool generic, bool di
 {
     PhiLaunchInfo li; memset(&li, 0, sizeof(li));
     li.kernel = kernel; li.generic = generic; li.dist = dist; li.adaptive = adaptive; li.masked = masked;
-    li.TY = c.TY; li.stages = c.R; li.ZC = c.ZC; li.nzc = c.nzc; li.groups = c.groups; li.total_units = c.total_units; li.grid_ctas = grid;
+    li.TY = c.TY; li.stages = c.R; li.ZC = c.ZC; li.nzc = c.nzc; li.groups = c.groups; li.total_units = c.total_units; li.grid_ctas = grid; li.split = c.split;
     phi_note_launch(li);
 }
 

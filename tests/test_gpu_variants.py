@@ -27,7 +27,8 @@ PER3 = (('periodic', 'periodic'),) * 3
 ZG3 = (('zg', 'zg'),) * 3
 WALL3 = ((0.0, 0.0),) * 3                                   # closed box: pressure boundary ZERO_GRADIENT -> no constant ghosts
 PER_WALL3 = (('periodic', 'periodic'), (0.0, 0.0), ('periodic', 'periodic'))
-FAST_SHAPES = [(256, 16, 12), (512, 8, 8), (256, 64, 48)]
+FAST_SHAPES = [(256, 16, 12), (512, 8, 8), (256, 128, 48)]
+MULTI = (256, 128, 48)          # with PHICUDA_RING_NZC=16: 16 y tiles (TY = 8 at nx = 256) x 16 chunks = 256 units per batch entry
 DX = (0.5, 0.25, 2.0)
 
 
@@ -65,8 +66,8 @@ def assert_fast(kernel, multi_unit=False):
 def test_laplace_fast_variant(res, bcname, batch):
     bc = {'periodic': PER3, 'zg': ZG3, 'per_zg': (('periodic', 'periodic'), ('zg', 'zg'), ('zg', 'zg'))}[bcname]
     rng = np.random.default_rng(31)
-    multi = res == (256, 64, 48) and batch == 2
-    with ring_nzc(12 if multi else 0):
+    multi = res == MULTI and batch == 2
+    with ring_nzc(16 if multi else 0):
         dom = ops.Domain(res, DX, batch)
         a = rng.standard_normal((batch,) + res).astype(np.float32)
         da = dom.centered_from_numpy(a)
@@ -87,12 +88,12 @@ def test_cg_fast_variant(res, vname):
     vbc = {'periodic': PER3, 'wall': WALL3, 'per_wall': PER_WALL3}[vname]
     rng = np.random.default_rng(32)
     batch = 2
-    multi = res == (256, 64, 48)
+    multi = res == MULTI
     rhs = rng.standard_normal((batch,) + res).astype(np.float32)
     rhs[1] *= 5.0
     A = O.poisson_matrix(res, DX, O.pressure_bc(vbc))
     rtol = 1e-3
-    with ring_nzc(12 if multi else 0):
+    with ring_nzc(16 if multi else 0):
         dom = ops.Domain(res, DX, batch, vbc=vbc)
         # (the closed 512 x 8 x 8 box with dx = (0.5, 0.25, 2) needs > 1000 iterations in the oracle as well)
         prm = ops.cg_params(vbc, rtol=rtol, atol=1e-5, max_iter=5000)
@@ -121,12 +122,12 @@ def test_cg_fast_variant_truncated_iterates(res, method):
     vbc = PER3
     rng = np.random.default_rng(33)
     batch = 2
-    multi = res == (256, 64, 48)
+    multi = res == MULTI
     rhs = rng.standard_normal((batch,) + res).astype(np.float32)
     rhs[1] *= 3.0
     A = O.poisson_matrix(res, DX, O.pressure_bc(vbc))
     solver = O.cg if method == 'CG' else O.cg_adaptive
-    with ring_nzc(12 if multi else 0):
+    with ring_nzc(16 if multi else 0):
         dom = ops.Domain(res, DX, batch, vbc=vbc)
         for k in (1, 2, 3, 4, 7):
             prm = ops.cg_params(vbc, rtol=1e-12, atol=0.0, max_iter=k, method=method)
@@ -149,9 +150,9 @@ def test_make_incompressible_fast_variant(res, vname):
     vbc = {'periodic': PER3, 'wall': WALL3}[vname]
     rng = np.random.default_rng(34)
     dx = tuple(100.0 / r for r in res)
-    multi = res == (256, 64, 48)
+    multi = res == MULTI
     v = [(0.1 * rng.standard_normal(s)).astype(np.float32) for s in O.staggered_shapes(res, vbc)]
-    with ring_nzc(12 if multi else 0):
+    with ring_nzc(16 if multi else 0):
         dom = ops.Domain(res, dx, 1, vbc=vbc)
         dv = dom.faces_from_numpy(v, vbc)
         prm = ops.cg_params(vbc, rtol=1e-5, atol=1e-5)
@@ -173,16 +174,16 @@ def test_masked_ring_cg_multi_unit(vname):
     """N4 on the TMA ring at a size with several units per persistent CTA: obstacles (one touching the boundary, one in the
     interior) against the oracle's masked projection (phi/physics/fluid.py:121-162, 197-202)."""
     vbc = {'periodic': PER3, 'wall': WALL3, 'per_wall': PER_WALL3}[vname]
-    res = (256, 64, 48)
+    res = MULTI
     dx = tuple(50.0 / r for r in res)
     rng = np.random.default_rng(36)
     acc = np.ones(res, np.float32)
-    acc[60:110, 18:40, 5:30] = 0
+    acc[60:110, 30:70, 5:30] = 0
     acc[0:12, 0:9, 40:48] = 0
     hard = O.hard_bcs_faces(acc, vbc)
     v = [(0.1 * rng.standard_normal(s)).astype(np.float32) for s in O.staggered_shapes(res, vbc)]
     vmask = [h.copy() for h in hard]
-    with ring_nzc(12):
+    with ring_nzc(16):
         dom = ops.Domain(res, dx, 1, vbc=vbc)
         dv = dom.faces_from_numpy(v, vbc)
         ops.mul_faces(dom, vbc, dv, dom.faces_from_numpy(vmask, vbc))
@@ -199,6 +200,60 @@ def test_masked_ring_cg_multi_unit(vname):
         np.testing.assert_allclose(got[c], v_ref[c], rtol=0, atol=2e-4 * max(np.abs(v[c]).max(), 1e-3))
     p = dom.centered_to_numpy(dp)
     assert np.abs(p[acc == 0]).max() == 0.0
+
+
+class ring_split:
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        self.old = os.environ.get('PHICUDA_RING_SPLIT')
+        os.environ['PHICUDA_RING_SPLIT'] = str(self.mode)
+
+    def __exit__(self, *exc):
+        if self.old is None:
+            os.environ.pop('PHICUDA_RING_SPLIT', None)
+        else:
+            os.environ['PHICUDA_RING_SPLIT'] = self.old
+
+
+@pytest.mark.parametrize('res', [(256, 128, 48), (512, 64, 40)])
+@pytest.mark.parametrize('vname', ['periodic', 'wall'])
+def test_cg_tail_split_decomposition(res, vname):
+    """The tail-split decomposition of the persistent CG kernel (CTA c < tiles marches planes [0, Zm) of tile c, the remaining CTAs
+    share the tails [Zm, nz)): chosen automatically when the tile count does not fill the CTAs - 512^3 and all 512-wide z-slabs of
+    the multi-GPU runs.  Forced here; must give the iterates of the default decomposition bit for bit (same per-cell arithmetic,
+    the dot products are summed per CTA in a fixed order - only that order differs) and agree with the oracle."""
+    vbc = {'periodic': PER3, 'wall': WALL3}[vname]
+    rng = np.random.default_rng(37)
+    rhs = rng.standard_normal((1,) + res).astype(np.float32)
+    A = O.poisson_matrix(res, DX, O.pressure_bc(vbc))
+    dom = ops.Domain(res, DX, 1, vbc=vbc)
+    outs = {}
+    for mode in (0, 1):
+        with ring_split(mode):
+            for k in (3, 4):
+                prm = ops.cg_params(vbc, rtol=1e-12, atol=0.0, max_iter=k)
+                got = dom.centered_to_numpy(ops.cg_poisson(dom, vbc, dom.centered_from_numpy(rhs), None, prm))
+                li = ops.last_launch_info()
+                assert li['kernel'] == _lib.KERNEL_CG_RING and li['generic'] == 0 and li['split'] == mode, li
+                outs[(mode, k)] = got
+    y = rhs[0] - rhs[0].mean()
+    for k in (3, 4):
+        ref = O.cg(A, y, np.zeros(res, np.float32), 1e-12, 0.0, k, None)['x'].reshape(res)
+        ref = ref - ref.mean()
+        for mode in (0, 1):
+            np.testing.assert_allclose(outs[(mode, k)], ref, rtol=0, atol=2e-5 * max(1.0, np.abs(ref).max()))
+        # the two decompositions differ only in the order the per-CTA partial sums are added
+        np.testing.assert_allclose(outs[(1, k)], outs[(0, k)], rtol=0, atol=1e-6 * max(1.0, np.abs(ref).max()))
+    with ring_split(1):
+        prm = ops.cg_params(vbc, rtol=1e-3, atol=1e-5, max_iter=5000)
+        got = dom.centered_to_numpy(ops.cg_poisson(dom, vbc, dom.centered_from_numpy(rhs), None, prm))
+        info = ops.read_results(dom)
+    ref = O.cg(A, y, np.zeros(res, np.float32), 1e-3, 1e-5, 5000, None)
+    assert info['converged'][0] == 1 and abs(int(info['iterations'][0]) - ref['iterations']) <= max(2, ref['iterations'] // 10)
+    xr = ref['x'].reshape(res); xr = xr - xr.mean()
+    np.testing.assert_allclose(got, xr, rtol=0, atol=20e-3 * np.abs(xr).max())
 
 
 def _plume_parity(res, steps, expect_fast):
