@@ -206,6 +206,18 @@ int phicuda_make_incompressible_f32(const PhiGrid* g, const PhiVBC* vbc, float* 
                                     const PhiCgParams* prm, PhiCgResult* result, void* workspace,
                                     size_t workspace_bytes, void* stream);
 
+/* ---- A1 for CenteredGrid velocities: wide stencil (phi/physics/fluid.py:154-155, 197-202) ---------------
+ * v: `dim` CENTRED arrays (component c with boundary vbc->comp[c]); div and grad are central differences
+ * (phi/field/_field_math.py:230-233, 627-632), the operator divergence(gradient(p)) is not symmetric at the boundary rows, so the
+ * solver is CG-adaptive (prm->method must be PHI_SOLVER_CG_ADAPTIVE = what Solve('auto') runs, PhiML backend/_linalg.py:93-128) with
+ * prm->matrix_offset = the reference's rank-1 offset for rank-deficient systems (_optimize.py:705-714; estimate it with
+ * phicuda_wide_laplace_f32 on a random vector).  p: in = x0, out = pressure.  Not the tuned path: simple kernels, and the call
+ * SYNCHRONISES the stream every few iterations to read the stopping flags (hence `_host`). */
+size_t phicuda_collocated_workspace_bytes(const PhiGrid* g);
+int phicuda_wide_laplace_f32(const PhiGrid* g, const PhiVBC* vbc, const float* x, float* y, void* workspace, size_t workspace_bytes, void* stream);
+int phicuda_make_incompressible_centered_host_f32(const PhiGrid* g, const PhiVBC* vbc, float* const v[3], float* p, const PhiCgParams* prm,
+                                                  PhiCgResult* result, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- N4  static obstacles (phi/physics/fluid.py:121-137, 165-202, 212-240) ---------------------------------------------
  * accessible: centred mask, 1 in fluid cells, 0 inside obstacles (`~union(obstacle geometries)` sampled at cell centres).
  * make_incompressible_masked = divergence * active, CG on masked_laplace (faces touching an obstacle carry no flux,

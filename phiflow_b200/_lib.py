@@ -79,6 +79,10 @@ PROTOTYPES = {
                                                   C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'phicuda_divergence_masked_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), F3, C.c_void_p, C.c_void_p, C.c_void_p]),
     'phicuda_grad_sub_masked_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), F3, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'phicuda_collocated_workspace_bytes': (C.c_size_t, [_P(PhiGrid)]),
+    'phicuda_wide_laplace_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'phicuda_make_incompressible_centered_host_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), F3, C.c_void_p, _P(PhiCgParams), C.c_void_p,
+                                                                C.c_void_p, C.c_size_t, C.c_void_p]),
     'phicuda_mul_faces_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), F3, F3, C.c_void_p]),
     'phicuda_cg_poisson_masked_f32': (C.c_int, [_P(PhiGrid), _P(PhiVBC), C.c_void_p, C.c_void_p, C.c_void_p, _P(PhiCgParams),
                                                 C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -360,6 +360,54 @@ def make_incompressible(dom: Domain, vbc, v, p=None, prm: PhiCgParams = None, ac
     return v, p
 
 
+def _collocated_workspace(dom: Domain):
+    if getattr(dom, '_co_ws', None) is None:
+        n = _lib.load().phicuda_collocated_workspace_bytes(C.byref(dom.grid))
+        dom._co_ws = torch.zeros(n, dtype=torch.uint8, device=dom.device)
+    return dom._co_ws
+
+
+def wide_laplace(dom: Domain, vbc, x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+    """fluid.masked_laplace(wide_stencil=True) without obstacles (phi/physics/fluid.py:197-202): centred divergence of the centred
+    gradient, the pressure operator of CenteredGrid velocities."""
+    require_cuda()
+    out = dom.alloc_centered() if out is None else out
+    ws = _collocated_workspace(dom)
+    _lib.check(_lib.load().phicuda_wide_laplace_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _ptr(x), _ptr(out), _ptr(ws),
+                                                    C.c_size_t(ws.numel()), _stream()))
+    return out
+
+
+def estimate_matrix_offset(dom: Domain, vbc, seed: int = 0) -> float:
+    """The rank-1 offset the reference adds to rank-deficient systems (PhiML/phiml/math/_optimize.py:705-714):
+    sqrt(mean|A x| * 9 / N) for a uniform random x - here with the wide-stencil operator."""
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    x = dom.alloc_centered()
+    idx = (slice(None),) + tuple(slice(0, dom.res[a]) for a in range(dom.dim - 1, -1, -1))
+    x[idx] = torch.rand((dom.batch,) + tuple(reversed(dom.res)), generator=g).to(dom.device)
+    y = wide_laplace(dom, vbc, x)
+    n = float(np.prod(dom.res))
+    return float(torch.sqrt(y[idx].abs().mean() * 9.0 / n).item())
+
+
+def make_incompressible_centered(dom: Domain, vbc, v: List[torch.Tensor], p: torch.Tensor = None, rtol=1e-5, atol=1e-5, max_iter=1000,
+                                 matrix_offset=None):
+    """fluid.make_incompressible for a CenteredGrid velocity (wide stencil, phi/physics/fluid.py:138-161 with :154-155): v = `dim`
+    CENTRED arrays, updated in place; returns (v, p).  Solver: CG-adaptive, what the reference's default Solve() runs.
+    Synchronises the stream (the iteration loop polls the stopping flags from the host)."""
+    require_cuda()
+    _, res = dom.workspace()
+    ws = _collocated_workspace(dom)
+    p = dom.alloc_centered() if p is None else p
+    prm = cg_params(vbc, rtol=rtol, atol=atol, max_iter=max_iter, method='CG-adaptive')
+    if prm.project_mean and matrix_offset is None:
+        matrix_offset = estimate_matrix_offset(dom, vbc)
+    prm.matrix_offset = float(matrix_offset or 0.0) if prm.project_mean else 0.0
+    _lib.check(_lib.load().phicuda_make_incompressible_centered_host_f32(C.byref(dom.grid), C.byref(make_vbc(vbc, dom.dim)), _f3(v), _ptr(p),
+                                                                        C.byref(prm), _ptr(res), _ptr(ws), C.c_size_t(ws.numel()), _stream()))
+    return v, p
+
+
 def plume_step(dom: Domain, vbc, sbc, v, s, p, inflow, dt, inflow_rate, buoyancy, prm: PhiCgParams, mac_cormack=False, cg_events=None,
                static_scalar=False):
     """incompressible_step: the notebook step (examples/grids/Smoke_Plume.ipynb:58-68) as one C-ABI call; state updated in place.

@@ -431,6 +431,52 @@ int phicuda_make_incompressible_f32(const PhiGrid* g, const PhiVBC* vbc, float* 
     return project(g, vbc, v, v, p, div, prm, result, workspace, workspace_bytes, nullptr, nullptr, stream);
 }
 
+// ---- CenteredGrid velocities (wide stencil) -------------------------------------------------------------------------------
+static int collocated_fields(const PhiGrid* g, const PhiVBC* vbc, DGrid* dg, DField vf[3], DField vf0[3], DField* pf, DField* cf)
+{
+    CHECK(phi_make_dgrid(g, dg));
+    if (g->halo != 0) { phi_set_error("collocated: z-slabs are not supported for CenteredGrid velocities"); return PHI_ERR_UNSUPPORTED; }
+    if (!vbc) { phi_set_error("collocated: boundary is NULL"); return PHI_ERR_INVALID; }
+    PhiBC none, pbc; memset(&none, 0, sizeof(none));
+    CHECK(phi_make_centered(g, &none, cf));
+    CHECK(phi_pressure_bc(vbc, g->dim, &pbc)); CHECK(phi_make_centered(g, &pbc, pf));
+    for (int c = 0; c < 3; ++c) {
+        if (c >= g->dim) { memset(&vf[c], 0, sizeof(DField)); memset(&vf0[c], 0, sizeof(DField)); continue; }
+        CHECK(phi_make_centered(g, &vbc->comp[c], &vf[c]));
+        PhiBC zero = vbc->comp[c];                               // extrapolation.remove_constant_offset (fluid.py:200)
+        for (int a = 0; a < 3; ++a) { zero.clo[a] = 0.f; zero.chi[a] = 0.f; }
+        CHECK(phi_make_centered(g, &zero, &vf0[c]));
+    }
+    return 0;
+}
+
+size_t phicuda_collocated_workspace_bytes(const PhiGrid* g)
+{
+    DGrid dg;
+    if (phi_make_dgrid(g, &dg)) return 0;
+    return phi_collocated_workspace_bytes(dg);
+}
+
+int phicuda_wide_laplace_f32(const PhiGrid* g, const PhiVBC* vbc, const float* x, float* y, void* workspace, size_t workspace_bytes, void* stream)
+{
+    DGrid dg; DField vf[3], vf0[3], pf, cf;
+    CHECK(collocated_fields(g, vbc, &dg, vf, vf0, &pf, &cf));
+    if (!x || !y || !workspace || x == y) { phi_set_error("wide_laplace: NULL / aliased argument"); return PHI_ERR_INVALID; }
+    return cuda_fail(phi_wide_laplace(dg, vf0, pf, cf, x, y, workspace, workspace_bytes, (cudaStream_t)stream), "wide_laplace");
+}
+
+int phicuda_make_incompressible_centered_host_f32(const PhiGrid* g, const PhiVBC* vbc, float* const v[3], float* p, const PhiCgParams* prm,
+                                                  PhiCgResult* result, void* workspace, size_t workspace_bytes, void* stream)
+{
+    DGrid dg; DField vf[3], vf0[3], pf, cf;
+    CHECK(collocated_fields(g, vbc, &dg, vf, vf0, &pf, &cf));
+    if (!v || !p || !prm || !result || !workspace) { phi_set_error("make_incompressible_centered: NULL argument"); return PHI_ERR_INVALID; }
+    for (int c = 0; c < g->dim; ++c) if (!v[c]) { phi_set_error("make_incompressible_centered: component %d is NULL", c); return PHI_ERR_INVALID; }
+    if (prm->method != PHI_SOLVER_CG_ADAPTIVE) { phi_set_error("make_incompressible_centered: the wide-stencil operator is not symmetric - use PHI_SOLVER_CG_ADAPTIVE (Solve('auto'))"); return PHI_ERR_UNSUPPORTED; }
+    return cuda_fail(phi_make_incompressible_collocated(dg, vf, vf0, pf, cf, v, p, *prm, prm->balance_rhs, result, workspace, workspace_bytes,
+                                                        (cudaStream_t)stream), "make_incompressible_centered");
+}
+
 static size_t centred_elems(const PhiGrid* g) { return (size_t)g->cext[0] * g->cext[1] * (g->dim == 3 ? g->cext[2] : 1) * g->batch; }
 static size_t face_elems(const PhiGrid* g) { return (size_t)g->fext[0] * g->fext[1] * (g->dim == 3 ? g->fext[2] : 1) * g->batch; }
 

@@ -26,6 +26,13 @@ int phi_launch_advect_centered_vec(const DGrid& g, const DVec& vel, const DField
 int phi_launch_advect_staggered_vec(const DGrid& g, const DVec& vel, const DVec& fld, const DVecOut& dst, float dt,
                                     const DField* sf, const float* sarr, const float bu[3], cudaStream_t s);
 int phi_launch_grid_sample(const DGrid& g, const DField& f, const float* grid, const float* coords, long long npoints, float* out, cudaStream_t s);
+// CenteredGrid (collocated) velocities, wide stencil (collocated_kernels.cu)
+size_t phi_collocated_workspace_bytes(const DGrid& g);
+int phi_make_incompressible_collocated(const DGrid& g, const DField vfields[3], const DField vfields0[3], const DField& pf, const DField& cf,
+                                       float* const v[3], float* p, const PhiCgParams& prm, int balance, PhiCgResult* result,
+                                       void* workspace, size_t ws_bytes, cudaStream_t s);
+int phi_wide_laplace(const DGrid& g, const DField vfields0[3], const DField& pf, const DField& cf, const float* x, float* y,
+                     void* workspace, size_t ws_bytes, cudaStream_t s);
 bool phi_scalar_kernels();      // PHICUDA_SCALAR_KERNELS=1: diagnostics, forces the one-thread-per-sample kernels of round 1
 
 struct CgLaunch {
