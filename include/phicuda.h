@@ -7,7 +7,9 @@
  * Conventions:
  *   - plain C types only; all array arguments are DEVICE pointers unless the name ends in `_host`;
  *   - functions enqueue work on `stream` (a cudaStream_t passed as void*) and return immediately;
- *     they never allocate, free or synchronise, except the `*_host` convenience calls which say so;
+ *     they never allocate, free or synchronise.  Exceptions, each saying so at its declaration: the `*_host` calls
+ *     (synchronise the stream) and the SET-UP calls of the multi-GPU communicator (phicuda_comm_create / _connect / _destroy:
+ *     cudaMalloc + cudaMemset + device synchronisation / CUDA-IPC open / cudaFree - once per run, never inside a step);
  *   - return 0 on success, a negative PHI_ERR_* or a positive cudaError_t otherwise; the message is kept per thread
  *     and read with phicuda_last_error();
  *   - fp32 only.  Other precisions are not part of this path (the reference falls through to its stock backends).
@@ -190,6 +192,9 @@ int phicuda_cg_poisson_f32(const PhiGrid* g, const PhiVBC* vbc, const float* rhs
  * exchanged as CUDA IPC handles (64 bytes each) by the caller (e.g. with torch.distributed.all_gather). */
 typedef struct PhiComm PhiComm;
 #define PHI_IPC_HANDLE_BYTES 64
+/* SET-UP calls (allocate / synchronise / free; see the conventions at the top): create allocates this rank's buffer and returns its
+ * IPC handle, connect opens the peers' handles, destroy closes them and frees the buffer.  The grid fixes the buffer layout: a
+ * communicator serves solves on exactly that PhiGrid (dist.SlabPlume rebuilds it when the halo is re-allocated). */
 int phicuda_comm_create(int rank, int nranks, const PhiGrid* g, PhiComm** comm, void* ipc_handle_out);
 int phicuda_comm_connect(PhiComm* comm, const void* all_handles /* nranks * 64 bytes, rank order */);
 int phicuda_comm_destroy(PhiComm* comm);

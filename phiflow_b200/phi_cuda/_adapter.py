@@ -260,6 +260,30 @@ def make_incompressible(values, ext, dx, dims: Sequence[str], resolution: Sequen
     return push_staggered(dom, v, vspec, batch_shape, dims), push_centered(dom, p, batch_shape, dims), info
 
 
+def make_incompressible_centered(values, ext, dx, dims: Sequence[str], resolution: Sequence[int], method='auto', rel_tol=1e-5, abs_tol=1e-5,
+                                 max_iterations=1000):
+    """fluid.make_incompressible for a CenteredGrid velocity (wide stencil, phi/physics/fluid.py:154-155): values = Tensor with a
+    channel dim `vector` over `dims`.  Only 'auto' / 'CG-adaptive' - the operator is not symmetric at the boundary rows and the
+    reference's plain CG does not converge on it either."""
+    reason = eligible(dims, ext, solve_method=method)
+    if reason:
+        raise NotEligible(reason)
+    if method not in ('auto', 'CG-adaptive'):
+        raise NotEligible(f"solver '{method}' on the wide-stencil (CenteredGrid) operator: fast path runs CG-adaptive only")
+    math, _ = _phiml()
+    vspec = to_vspec(ext, dims)
+    comps = [values.vector[d] for d in dims]
+    batch_shape = _batch_of(*comps)
+    dom = _domain(tuple(resolution), _dx_tuple(dx, dims), max(1, batch_shape.volume), None)
+    v = [pull_centered(dom, c, batch_shape, dims) for c in comps]
+    v, p = ENGINE.make_incompressible_centered(dom, vspec, v, None, rtol=rel_tol, atol=abs_tol, max_iter=max_iterations)
+    res = ENGINE.read_results(dom)
+    info = {k: np.array(res[k]) for k in ('iterations', 'converged', 'diverged', 'residual_sq', 'tol_sq')}
+    from phiml.math import channel
+    out = math.stack([push_centered(dom, t, batch_shape, dims) for t in v], channel(vector=tuple(dims)))
+    return out, push_centered(dom, p, batch_shape, dims), info
+
+
 def semi_lagrangian_staggered(values, ext, velocity_values, velocity_ext, dx, dims, resolution, dt: float):
     """advect.semi_lagrangian of a StaggeredGrid by a StaggeredGrid on the same grid (phi/physics/advect.py:156-179)."""
     reason = eligible(dims, velocity_ext) or eligible(dims, ext)

@@ -63,8 +63,19 @@ def make_incompressible(velocity, obstacles=(), solve=Solve(), active=None, orde
     """fluid.make_incompressible (phi/physics/fluid.py:94-100), fast path for StaggeredGrids on uniform grids."""
     stock = _fluid.make_incompressible
     try:
-        if not isinstance(velocity, _Field) or not velocity.is_staggered:
-            raise NotEligible("CenteredGrid velocity / not a grid")
+        if not isinstance(velocity, _Field) or not velocity.is_grid:
+            raise NotEligible("not a grid")
+        if not velocity.is_staggered:            # CenteredGrid velocity: wide stencil, CG-adaptive only (fluid.py:154-155)
+            dims, res, dx = _grid_info(velocity)
+            if _fluid._get_obstacles_for(obstacles, velocity) or active is not None or order != 2 or correct_skew or wide_stencil is False \
+                    or solve.x0 is not None or solve.preconditioner is not None:
+                raise NotEligible("CenteredGrid velocity with obstacles / active / x0 / narrow stencil")
+            values, p, info = _adapter.make_incompressible_centered(velocity.values, velocity.extrapolation, dx, dims, res, method=solve.method,
+                                                                    rel_tol=float(solve.rel_tol), abs_tol=float(solve.abs_tol),
+                                                                    max_iterations=int(_math.max(solve.max_iterations)))
+            pressure = _CenteredGrid(p, _fluid._pressure_extrapolation(velocity.extrapolation), velocity.bounds, velocity.resolution)
+            _report(solve, info, pressure)
+            return velocity.with_values(values), pressure
         dims, res, dx = _grid_info(velocity)
         reason = _adapter.eligible(dims, velocity.extrapolation, order=order, solve_method=solve.method, obstacles=_fluid._get_obstacles_for(obstacles, velocity),
                                    active=active, preconditioner=solve.preconditioner)

@@ -66,6 +66,18 @@ class FakeOps:
         cls.last = rec
 
     @classmethod
+    def make_incompressible_centered(cls, dom, vspec, v, p, rtol=1e-5, atol=1e-5, max_iter=1000, matrix_offset=None):
+        comps = [dom.centered_to_numpy(t, squeeze=False) for t in v]
+        outs, ps, rec = [], [], np.zeros(dom.batch, dtype=_ops._RESULT_DTYPE)
+        for b in range(dom.batch):
+            vb, pb, info = O.make_incompressible_centered([c[b] for c in comps], vspec, dom.res, dom.dx, rtol, atol, max_iter)
+            outs.append(vb); ps.append(pb)
+            rec[b] = (info['iterations'], int(info['converged']), int(info['diverged']), info['residual_sq'], info['tol_sq'], 0.0)
+        cls.last = rec
+        new = [dom.centered_from_numpy(np.stack([o[c] for o in outs])) for c in range(dom.dim)]
+        return new, dom.centered_from_numpy(np.stack(ps))
+
+    @classmethod
     def read_results(cls, dom):
         return cls.last
 
@@ -248,6 +260,33 @@ def test_make_incompressible_with_phiml_tensors(fake_engine, name):
     with math.precision(64):
         with pytest.raises(A.NotEligible):
             A.make_incompressible(values, ext, dx, dims, res, method='CG')
+
+
+@pytest.mark.parametrize('name', ['zero', 'boundary'])
+def test_make_incompressible_centered_velocity_with_phiml_tensors(fake_engine, name):
+    """tests/commit/physics/test_fluid.py:34-36: CenteredGrid velocity (channel dim `vector`), ZERO and BOUNDARY; result checked with
+    the reference's own centred divergence (math.spatial_gradient 'central' + padding by the velocity boundary, _field_math.py:627-632)."""
+    dims, res = ('x', 'y'), (16, 20)
+    ext = {'zero': E.ZERO, 'boundary': E.BOUNDARY}[name]
+    dx = {'x': 100.0 / 16, 'y': 100.0 / 20}
+    # the reference test's input: buoyancy of a sphere of smoke (smooth; white noise has components outside the range of the
+    # singular wide-stencil operator and cannot be projected to 5e-5)
+    pts = O.points_of((0.0, 0.0), (100.0, 100.0), res)
+    a = np.zeros((2, 16, 20, 2), np.float32)
+    for b, centre in enumerate(((40.0, 10.0), (55.0, 30.0))):
+        a[b, :, :, 1] = 0.1 * (np.sum((pts - np.array(centre, np.float32)) ** 2, -1) <= 25.0)
+    values = math.tensor(a, batch(b=2) & spatial(x=16, y=20) & channel(vector='x,y'))
+    new_values, pressure, info = A.make_incompressible_centered(values, ext, dx, dims, res, method='auto')
+    assert set(new_values.shape.names) == {'b', 'x', 'y', 'vector'} and new_values.shape.get_item_names('vector') == ('x', 'y')
+    assert set(pressure.shape.names) == {'b', 'x', 'y'} and not info['diverged'].any()
+    div = 0
+    for d in dims:
+        comp = new_values.vector[d]
+        padded = math.pad(comp, {d: (1, 1)}, ext)
+        div = div + (padded[{d: slice(2, None)}] - padded[{d: slice(None, -2)}]) / (2 * dx[d])
+    assert float(np.abs(div.numpy(div.shape.names)).max()) < 5e-5
+    with pytest.raises(A.NotEligible):
+        A.make_incompressible_centered(values, ext, dx, dims, res, method='CG')       # plain CG: not on this operator
 
 
 def test_semi_lagrangian_and_stencils_with_phiml_tensors(fake_engine):
