@@ -118,6 +118,8 @@ static int cg_dist(const PhiGrid* g, const PhiVBC* vbc, const float* rhs, float*
         cm.flag[q] = (unsigned long long*)(c->peer[q] + c->off_flags);
     }
     cm.seq = (unsigned long long*)(c->local + c->off_seq);
+    cm.arrive = (unsigned*)(c->local + c->off_seq + 64);
+    { cudaError_t ce = cudaMemsetAsync(cm.arrive, 0, sizeof(unsigned), (cudaStream_t)stream); if (ce != cudaSuccess) { phi_set_error("cg_dist: memset failed: %s", cudaGetErrorString(ce)); return (int)ce; } }
     const size_t hoff = (size_t)g->halo * g->cext[0] * g->cext[1];
     auto vec = [&](int q, int k) -> float* { return (float*)(c->peer[q] + c->off_ws + (size_t)k * c->arr_bytes) + hoff; };
     if (cm.lower >= 0) { cm.lo_r = vec(cm.lower, 0); cm.lo_d0 = vec(cm.lower, 1); cm.lo_d1 = vec(cm.lower, 2); }

@@ -753,6 +753,7 @@ struct CgRingArgs {
     CgArgs a;
     RingCfg cfg;
     int ring_smem_offset;        // byte offset of the ring inside dynamic shared memory (after the CgShared block)
+    int comm_merge;              // multi-GPU: 1 = merged barrier + all-reduce (comm_barrier_allreduce), 0 = grid.sync + comm_allreduce
     CommDev cm;
 };
 
@@ -776,6 +777,58 @@ __device__ __forceinline__ bool comm_allreduce(const CommDev& cm, const CgShared
     const int par = (int)(seq & 1ull);
     const size_t stride = 2 * (size_t)CG_MAX_BATCH;
     if (blockIdx.x == 0) {
+        for (int q = 0; q < cm.n; ++q) {
+            double* dst = cm.mbox[q] + ((size_t)par * PHI_MAX_RANKS + cm.rank) * stride;
+            for (int b = threadIdx.x; b < batch; b += blockDim.x) { dst[b] = sh.sum0[b]; dst[CG_MAX_BATCH + b] = sh.sum1[b]; }
+        }
+        __threadfence_system();
+        __syncthreads();
+        if ((int)threadIdx.x < cm.n) st_release_sys(cm.flag[threadIdx.x] + par * PHI_MAX_RANKS + cm.rank, seq);
+    }
+    bool ok = true;
+    if ((int)threadIdx.x < cm.n) {
+        const unsigned long long* f = cm.flag[cm.rank] + par * PHI_MAX_RANKS + threadIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < seq) {
+            if (clock64() - t0 > 40000000000ll) { ok = false; break; }        // ~20 s: a peer died; do not hang the GPU
+        }
+    }
+    ok = __syncthreads_and(ok);
+    const double* src = cm.mbox[cm.rank] + (size_t)par * PHI_MAX_RANKS * stride;
+    for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+        double s0 = 0, s1 = 0;
+        for (int q = 0; q < cm.n; ++q) {
+            s0 += *(volatile const double*)(src + q * stride + b);
+            s1 += *(volatile const double*)(src + q * stride + CG_MAX_BATCH + b);
+        }
+        sh.sum0[b] = s0; sh.sum1[b] = s1;
+    }
+    __syncthreads();
+    return ok;
+}
+
+// Merged barrier + all-reduce of the multi-GPU kernels (PHICUDA_COMM_MERGE=0 restores grid.sync + comm_allreduce).
+// Every CTA makes its stores visible system-wide (partial sums, halo planes stored into the neighbours' memory) and arrives on a
+// local counter; the LAST CTA to arrive sums the per-CTA partials in a fixed order and sends the result with a release flag to
+// every rank (itself included); every CTA of every rank then waits for the n flags in its own mailbox and adds the n entries in
+// rank order.  One arrival + one flag hop instead of a full grid barrier followed by block 0's send: the local release of the
+// grid barrier, the redundant partial reduction in all CTAs and block 0's serial send are gone.  The own rank's flag is only
+// written after all local CTAs arrived, so passing the wait still implies "every local CTA finished the pass".
+__device__ __forceinline__ bool comm_barrier_allreduce(const CommDev& cm, const CgShared& sh, const double* partials, int region, int batch,
+                                                       int units_per_batch, const unsigned char* active, unsigned long long seq)
+{
+    const int par = (int)(seq & 1ull);
+    const size_t stride = 2 * (size_t)CG_MAX_BATCH;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(cm.arrive, 1u);
+        sh.any_cont[1] = ((prev + 1u) % gridDim.x == 0u) ? 1 : 0;
+    }
+    __syncthreads();
+    if (sh.any_cont[1]) {                                    // CTA-uniform: the last arriver
+        __threadfence();
+        reduce_partials(sh, partials, region, batch, units_per_batch, active);
         for (int q = 0; q < cm.n; ++q) {
             double* dst = cm.mbox[q] + ((size_t)par * PHI_MAX_RANKS + cm.rank) * stride;
             for (int b = threadIdx.x; b < batch; b += blockDim.x) { dst[b] = sh.sum0[b]; dst[CG_MAX_BATCH + b] = sh.sum1[b]; }
@@ -861,6 +914,12 @@ k_cg_ring(CgRingArgs A)
     bool comm_ok = true;
     auto barrier_and_reduce = [&](const unsigned char* active) {
         fence_proxy_async();                       // generic-proxy stores of this pass -> later TMA (async proxy) loads
+        if (DIST && cm.n > 1 && A.comm_merge) {    // merged barrier + all-reduce
+            comm_ok = comm_barrier_allreduce(cm, sh, a.partials, region, batch, cfg.split ? (int)gridDim.x : cfg.units_per_batch, active, ++seq) && comm_ok;
+            region ^= 1;
+            fence_proxy_async();
+            return;
+        }
         if (cm.n > 1) __threadfence_system();      // halo planes stored into the neighbours' memory
         grid.sync();
         fence_proxy_async();
@@ -1249,6 +1308,7 @@ int phi_launch_cg_ring(const CgLaunch& l, const CommDev* cm, cudaStream_t s)
     a.partials = (double*)(ws + 3 * arr);
     a.result = l.result; a.prm = l.prm;
     if (cm) A.cm = *cm; else { memset(&A.cm, 0, sizeof(A.cm)); A.cm.n = 1; A.cm.lower = A.cm.upper = -1; }
+    { const char* e = getenv("PHICUDA_COMM_MERGE"); A.comm_merge = (e && e[0] == '0') ? 0 : 1; }
     void* args[] = {&A};
     e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, smem, s);
     if (e != cudaSuccess) { phi_set_error("cg ring: cooperative launch failed: %s", cudaGetErrorString(e)); return (int)e; }
