@@ -349,7 +349,7 @@ def grid_sample_native(grid: torch.Tensor, coords: torch.Tensor, mode: str):
     (batch, points..., d) in index space, mode in 'zeros' | 'boundary' | 'periodic'.  Anything else -> NotImplemented, the
     reference then runs its own fallback (_ops.py:983-1015)."""
     spec_side = {'zeros': 0.0, 'boundary': 'zg', 'periodic': 'periodic'}.get(mode)
-    if spec_side is None or grid.dtype != torch.float32 or not grid.is_cuda:
+    if spec_side is None or grid.dtype != torch.float32 or grid.device.type != torch.device(DEVICE).type:
         return NotImplemented
     d = grid.dim() - 2
     if d not in (2, 3) or coords.shape[-1] != d:

@@ -53,7 +53,7 @@ class PhiCudaBackend(TorchBackend):
 
     def grid_sample(self, grid, coordinates, extrapolation: str):
         grid, coordinates = self.as_tensor(grid), self.as_tensor(coordinates)
-        if isinstance(grid, torch.Tensor) and grid.is_cuda:
+        if isinstance(grid, torch.Tensor) and grid.device.type == torch.device(_adapter.DEVICE).type:
             result = _adapter.grid_sample_native(grid, coordinates.to(grid.device), extrapolation)
             if result is not NotImplemented:
                 return result

@@ -1,10 +1,11 @@
 """
 Reference-side adapter (phiflow_b200/phi_cuda, row B1) against REAL phiml objects from the vendored PhiML 1.7.2
-(/root/reference/PhiML; skipped where it is absent, e.g. on the GPU box): boundary translation, named-dim layouts incl. the
+(baseline/_ref as installed by __graft_entry__.build(), else /root/reference/PhiML): boundary translation, named-dim layouts incl. the
 non-uniform staggered TensorStack, the eligibility matrix of SURVEY.md section 3.4, and the hot-path functions with phiml Tensors
 in and out.  There is no GPU here, so the compute engine is replaced by an oracle-backed stand-in with the SAME interface as
 phiflow_b200._ops (device arrays in, device arrays updated in place) - this file tests the plumbing around the C ABI, the
-kernels themselves are tested against the oracle in the -m gpu tests.
+kernels themselves are tested against the oracle in the -m gpu tests, and tests/test_gpu_phi_cuda.py repeats this file's cases
+with the real engine against the reference library run live.
 """
 import os
 import sys
@@ -13,11 +14,10 @@ import numpy as np
 import pytest
 import torch
 
-PHIML = '/root/reference/PhiML'
-if not os.path.isdir(PHIML):
-    pytest.skip('vendored PhiML not available (reference tree absent)', allow_module_level=True)
-if PHIML not in sys.path:
-    sys.path.insert(0, PHIML)
+from _phiml import ensure_phiml  # noqa: E402
+
+if not ensure_phiml(allow_reference_tree=True):
+    pytest.skip('PhiML not available (neither baseline/_ref nor the reference tree)', allow_module_level=True)
 
 from phiml import math  # noqa: E402
 from phiml.math import extrapolation as E, spatial, batch, dual, channel  # noqa: E402
@@ -99,6 +99,26 @@ class FakeOps:
     def laplace(cls, dom, spec, x):
         a = dom.centered_to_numpy(x, squeeze=False)
         return dom.centered_from_numpy(np.stack([O.laplace(a[b], dom.dx, spec) for b in range(dom.batch)]))
+
+    @classmethod
+    def grid_sample(cls, dom, bc, grid, coords):
+        g = dom.centered_to_numpy(grid, squeeze=False)                     # (batch, x, y[, z])
+        c = coords.numpy()
+        return torch.from_numpy(np.stack([O.grid_sample(g[b], c[b], bc) for b in range(dom.batch)]).astype(np.float32))
+
+    @classmethod
+    def cg_poisson(cls, dom, vspec, rhs, x, prm):
+        y, x0 = dom.centered_to_numpy(rhs, squeeze=False), dom.centered_to_numpy(x, squeeze=False)
+        Amat = O.poisson_matrix(dom.res, dom.dx, O.pressure_bc(vspec))
+        solver = O.cg_adaptive if prm.method == 1 else O.cg
+        rec, xs = np.zeros(dom.batch, dtype=_ops._RESULT_DTYPE), []
+        for b in range(dom.batch):
+            info = solver(Amat, y[b], x0[b], prm.rtol, prm.atol, prm.max_iter, None)
+            xs.append(info['x'].reshape(dom.res))
+            rec[b] = (info['iterations'], int(info['converged']), int(info['diverged']), info['residual_sq'], info['tol_sq'], 0.0)
+        cls.last = rec
+        x.copy_(dom.centered_from_numpy(np.stack(xs)))
+        return x
 
     @classmethod
     def divergence(cls, dom, vspec, v):
@@ -326,16 +346,69 @@ def test_backend_registration_and_fall_through(fake_engine):
     y = torch.tensor([[1.0, 2.0]])
     res = b.linear_solve('CG', mat, y, torch.zeros_like(y), np.array([1e-6]), np.array([1e-6]), np.array([[100]]), None, None)
     np.testing.assert_allclose(np.asarray(res.x)[0], np.linalg.solve(mat.numpy(), y.numpy()[0]), atol=1e-4)
-    # grid_sample on tensors the fast path does not own (CPU) -> exactly what the stock torch backend answers (values or
-    # NotImplemented, after which phiml runs its own fallback, _ops.py:983-1015)
+    # grid_sample on tensors the fast path does not own (fp64: never downcast) -> exactly what the stock torch backend answers
+    # (values or NotImplemented, after which phiml runs its own fallback, _ops.py:983-1015); fp32 on the engine's device -> the plugin
     from phiml.backend.torch._torch_backend import TorchBackend
     grid = torch.arange(12, dtype=torch.float32).reshape(1, 4, 3, 1)
     pts = torch.tensor([[[0.5, 0.0], [1.5, 1.0], [2.25, 1.5]]])
-    out, stock = b.grid_sample(grid, pts, 'boundary'), TorchBackend.grid_sample(b, grid, pts, 'boundary')
-    if stock is NotImplemented:
-        assert out is NotImplemented
-    else:
-        np.testing.assert_allclose(np.asarray(out).ravel(), np.asarray(stock).ravel(), atol=1e-6)
-        np.testing.assert_allclose(np.asarray(out).ravel(), [1.5, 5.5, 8.25], atol=1e-5)
+    np.testing.assert_allclose(np.asarray(b.grid_sample(grid, pts, 'boundary')).ravel(), [1.5, 5.5, 8.25], atol=1e-5)
+    with math.precision(64):                     # (under precision 32 the torch backend itself casts fp64 natives to fp32)
+        out, stock = b.grid_sample(grid.double(), pts.double(), 'boundary'), TorchBackend.grid_sample(b, grid.double(), pts.double(), 'boundary')
+        if stock is NotImplemented:
+            assert out is NotImplemented
+        else:
+            assert out.dtype == torch.float64
+            np.testing.assert_allclose(np.asarray(out).ravel(), np.asarray(stock).ravel(), atol=1e-12)
+    assert A.grid_sample_native(grid, pts, 'symmetric') is NotImplemented
+    assert A.grid_sample_native(grid.double(), pts.double(), 'boundary') is NotImplemented
     with pytest.raises(NotImplementedError):
         b.linear_solve('biCG-stab(2)', PoissonOperator((4, 4), (1.0, 1.0), A.to_vspec(E.ZERO, ('x', 'y'))), y, y, [1e-5], [1e-5], np.array([[10]]), None, None)
+
+
+# ---- phiml's own dispatch: math.grid_sample / Backend.linear_solve reach the plugin -----------------------------------------------------
+@pytest.mark.parametrize('ext', [E.ZERO, E.ZERO_GRADIENT, E.PERIODIC], ids=['zeros', 'boundary', 'periodic'])
+@pytest.mark.parametrize('res', [(9, 7), (6, 5, 4)], ids=['2d', '3d'])
+def test_math_grid_sample_dispatches_to_the_plugin(fake_engine, monkeypatch, res, ext):
+    """PhiML/phiml/math/_ops.py:973-1003: with phicuda as the default backend, math.grid_sample hands the native grid
+    (batch, x, y[, z], channel) and coordinates (batch, points, d) to PhiCudaBackend.grid_sample.  Reference: the same call on
+    the stock NumPy backend."""
+    from phiml.math import instance
+    from phiflow_b200.phi_cuda._backend import get_backend
+    calls = []
+    real = A.grid_sample_native
+    monkeypatch.setattr(A, 'grid_sample_native', lambda g, c, m: calls.append(m) or real(g, c, m))
+    d = len(res)
+    names = 'xyz'[:d]
+    rng = np.random.default_rng(d)
+    g = rng.standard_normal((2,) + res + (2,)).astype(np.float32)
+    c = (rng.random((2, 40, d)) * (np.array(res) + 3.0) - 2.0).astype(np.float32)
+    gshape = batch(b=2) & spatial(**dict(zip(names, res))) & channel(comp=2)
+    cshape = batch(b=2) & instance(points=40) & channel(vector=','.join(names))
+    ref = math.grid_sample(math.tensor(g, gshape), math.tensor(c, cshape), ext)
+    with get_backend():
+        out = math.grid_sample(math.tensor(g, gshape, convert=True), math.tensor(c, cshape, convert=True), ext)
+    assert calls == [ext.native_grid_sample_mode]
+    assert isinstance(out.native(out.shape), torch.Tensor)
+    np.testing.assert_allclose(out.numpy('b,points,comp'), ref.numpy('b,points,comp'), atol=1e-5)
+
+
+@pytest.mark.parametrize('method', ['CG', 'CG-adaptive'])
+def test_backend_linear_solve_with_poisson_operator(fake_engine, method):
+    """Same system through the reference's solver (phiml NUMPY backend = _linalg.py unmodified) and through
+    PhiCudaBackend.linear_solve with the PoissonOperator tag: natives are (batch, cells) in the reference's x-outermost order."""
+    from phiml.backend import NUMPY
+    from phiflow_b200.phi_cuda._backend import get_backend, PoissonOperator
+    res, dx = (12, 10), (1.0, 0.5)
+    vbc = ((0.0, 0.0), (0.0, 'zg'))
+    Amat = O.poisson_matrix(res, dx, O.pressure_bc(vbc))
+    y = np.random.default_rng(2).standard_normal((2, 120)).astype(np.float32)
+    x0 = np.zeros_like(y)
+    tol, mi = np.full(2, 1e-5, np.float32), np.full((1, 2), 1000)
+    ref = NUMPY.linear_solve(method, Amat, y, x0, tol, tol, mi, None, None)
+    got = get_backend().linear_solve(method, PoissonOperator(res, dx, vbc), torch.from_numpy(y), torch.from_numpy(x0), tol, tol, mi, None, None)
+    assert 'phicuda' in got.method
+    # the reference's batched run rounds differently from its own single-entry run (strided sums over the transposed matvec result:
+    # entry 1 stops at 50 iterations in a batch of two, at 49 alone), the stand-in solves entry by entry
+    assert np.abs(np.asarray(got.iterations) - np.asarray(ref.iterations)).max() <= 1
+    np.testing.assert_allclose(got.x.numpy(), np.asarray(ref.x), atol=2e-5 * np.abs(ref.x).max())
+    assert np.asarray(got.converged).all()
