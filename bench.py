@@ -83,6 +83,60 @@ def cpu_plume(n: int, steps: int, warmup: int):
             "cg_iterations_per_step": float(np.mean(iters))}
 
 
+def reference_library_check(n: int = 64):
+    """How the port compares with the reference LIBRARY itself, run live: where baseline/_ref holds the unmodified PhiML that
+    `__graft_entry__.build()` installs, one pressure system of the plume at n^3 is solved by the oracle port's CG and by
+    `phiml.backend.NUMPY.linear_solve('CG', ...)` (= PhiML/phiml/backend/_linalg.py:23-89, what the reference's NumPy path runs), and
+    n^3 points are gathered by the port's grid_sample and by `phiml.math.grid_sample`.  Reports both times, the iteration counts and
+    whether the results are identical - the evidence that timing the port does not flatter the GPU arm.  None when PhiML is absent."""
+    ref_dir = os.path.join(ROOT, 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(ref_dir, 'phiml')):
+        return None
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    import warnings
+    from oracle import oracle_np as O
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        from phiml import math
+        from phiml.backend import NUMPY
+        from phiml.math import spatial, instance, channel, extrapolation as E
+        res = (n, n, n)
+        dx = tuple(100.0 / n for _ in range(3))
+        lower, upper = (0.0,) * 3, (100.0,) * 3
+        vbc = O.uniform_bc(3, O.PERIODIC)
+        A = O.poisson_matrix(res, dx, O.pressure_bc(vbc))
+        blob = O.sphere_soft_mask((50.0, 50.0, 30.0), 20.0, lower, upper, res)
+        v = [np.zeros(s, np.float32) for s in O.staggered_shapes(res, vbc)]
+        v[2] += 0.05 * (blob + np.roll(blob, 1, 2))                      # buoyancy of a smoke blob, as in the plume
+        y = O.divergence_staggered(v, dx, O.component_bcs(vbc, 3))
+        y = (y - y.mean(dtype=np.float32)).astype(np.float32)
+        t0 = time.perf_counter()
+        port = O.cg(A, y, np.zeros(res, np.float32), RTOL, ATOL, MAX_ITER, None)
+        t_port = time.perf_counter() - t0
+        yy = y.reshape(1, -1)
+        t0 = time.perf_counter()
+        ref = NUMPY.linear_solve('CG', A, yy, np.zeros_like(yy), np.array([RTOL], np.float32), np.array([ATOL], np.float32),
+                                 np.array([[MAX_ITER]]), None, None)
+        t_ref = time.perf_counter() - t0
+        rng = np.random.default_rng(0)
+        pts = (rng.random((n ** 3, 3)) * (n + 2.0) - 1.0).astype(np.float32)
+        g = rng.standard_normal(res).astype(np.float32)
+        t0 = time.perf_counter()
+        a = O.grid_sample(g, pts, O.uniform_bc(3, O.ZG))
+        t_gs_port = time.perf_counter() - t0
+        gt = math.tensor(g, spatial(x=n, y=n, z=n))
+        ct = math.tensor(pts, instance(points=n ** 3) & channel(vector='x,y,z'))
+        t0 = time.perf_counter()
+        b = math.grid_sample(gt, ct, E.ZERO_GRADIENT).numpy('points')
+        t_gs_ref = time.perf_counter() - t0
+    return {"library": "PhiML 1.7.2 (unmodified, baseline/_ref), NumPy backend", "grid": n,
+            "cg": {"port_s": t_port, "phiml_s": t_ref, "iterations_port": int(port['iterations']),
+                   "iterations_phiml": int(np.asarray(ref.iterations)[0]),
+                   "bitwise_equal": bool(np.array_equal(np.asarray(ref.x)[0], port['x'].reshape(-1)))},
+            "grid_sample": {"points": n ** 3, "port_s": t_gs_port, "phiml_s": t_gs_ref, "max_abs_diff": float(np.abs(a - b).max())}}
+
+
 # CG iterations per step of the SAME algorithm on the full grid, measured on the GPU by the driver (BENCH_r01.json: 512^3,
 # --steps 20 --warmup 5 -> 641.45; this round's builder runs agree to a few iterations).  The iteration count is a property
 # of the algorithm and the data (both arms run unpreconditioned CG to the same tolerance), so the CPU extrapolation uses it when
@@ -120,7 +174,8 @@ def cpu_report(sizes, steps, warmup, full, it_full=None):
     # a single cold step above (minutes per step)
     samples = [cpu_plume(n, steps, warmup) if i == 0 else (cpu_plume(n, 2, 1) if n < 200 else cpu_plume(n, 1, 0)) for i, n in enumerate(sizes)]
     t_full, it_full, law = extrapolate(samples, full, it_full)
-    return {"value": 1.0 / t_full, "unit": "steps/s", "cores": 1, "kind": "port", "extrapolated": True,
+    return {"reference_library_check": reference_library_check(),
+            "value": 1.0 / t_full, "unit": "steps/s", "cores": 1, "kind": "port", "extrapolated": True,
             "extrapolation": f"{law}; {t_full:.1f} s/step",
             "samples": samples,
             "sample": "the same plume on " + ", ".join(f"{s['grid']}^3 ({s['steps']} steps, {s['s_per_step']:.2f} s/step, {s['cg_iterations_per_step']:.0f} it)"

@@ -142,7 +142,7 @@ def push_centered(dom, dev: torch.Tensor, batch_shape, dims, like=None):
     from phiml.math import spatial
     idx = (slice(None),) + tuple(slice(0, dom.res[a]) for a in range(dom.dim - 1, -1, -1))
     groups = [batch_shape] + [spatial(**{d: dom.res[a]}) for a, d in reversed(list(enumerate(dims)))]
-    return math.reshaped_tensor(dev[idx].contiguous(), groups)
+    return math.reshaped_tensor(dev[idx].contiguous(), groups, convert=False)    # results stay on the device (no silent D2H copy)
 
 
 def split_components(values, dims: Sequence[str]):
@@ -183,7 +183,7 @@ def push_staggered(dom, dev: Sequence[torch.Tensor], vspec, batch_shape, dims):
             start = offsets[c] if ax == c else 0
             idx.append(slice(start, start + shapes[c][ax]))
         groups = [batch_shape] + [spatial(**{d: shapes[c][a]}) for a, d in reversed(list(enumerate(dims)))]
-        comps.append(math.reshaped_tensor(dev[c][tuple(idx)].contiguous(), groups))
+        comps.append(math.reshaped_tensor(dev[c][tuple(idx)].contiguous(), groups, convert=False))
     return math.stack(comps, dual(vector=tuple(dims)))
 
 
