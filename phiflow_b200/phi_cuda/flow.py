@@ -50,10 +50,21 @@ def _fall(name, reason, stock, *args, **kwargs):
 
 
 def _report(solve, info, x):
-    """SolveTape / NotConverged / Diverged protocol of math.solve_linear (PhiML/phiml/math/_optimize.py:190-204, 735-743)."""
+    """SolveTape / NotConverged / Diverged protocol of math.solve_linear (PhiML/phiml/math/_optimize.py:190-204, 735-743).
+    `x` is the pressure Field; the per-entry records of the kernel become Tensors over its batch dims.  The kernel keeps |r|^2 per
+    entry, not the residual vector: `SolveInfo.residual` holds the residual NORM per entry (the "Max residual" of the not-converged
+    message is then that norm)."""
+    import numpy as _np
     from phiml.math._optimize import SolveInfo, _SOLVE_TAPES
-    res = SolveInfo(solve, x, None, _math.wrap(info['iterations']), _math.wrap(info['iterations'] + 1), _math.wrap(info['converged'].astype(bool)),
-                    _math.wrap(info['diverged'].astype(bool)), "phicuda", None, None)
+    batch_shape = x.values.shape.batch
+
+    def per_entry(a):
+        a = _np.asarray(a)
+        return _math.reshaped_tensor(a, [batch_shape], convert=False) if batch_shape.rank else _math.wrap(a.reshape(-1)[0])
+    # one non-batch dim, so that per-entry slices stay Tensors like a real residual vector does (_optimize.py:207-214)
+    residual = _math.expand(per_entry(_np.sqrt(_np.maximum(info['residual_sq'], 0.0))), _math.channel(l2_norm=1))
+    res = SolveInfo(solve, x, residual, per_entry(info['iterations']), per_entry(info['iterations'] + 1),
+                    per_entry(info['converged'].astype(bool)), per_entry(info['diverged'].astype(bool)), "phicuda", None, None)
     for tape in _SOLVE_TAPES:
         tape._add(solve, False, res)
     res.convergence_check(False)          # raises NotConverged / Diverged unless suppressed by the Solve
@@ -62,9 +73,11 @@ def _report(solve, info, x):
 def make_incompressible(velocity, obstacles=(), solve=Solve(), active=None, order=2, correct_skew=False, wide_stencil=None):  # noqa: F405
     """fluid.make_incompressible (phi/physics/fluid.py:94-100), fast path for StaggeredGrids on uniform grids."""
     stock = _fluid.make_incompressible
+    original_solve = solve
     try:
         if not isinstance(velocity, _Field) or not velocity.is_grid:
             raise NotEligible("not a grid")
+        solve = solve.with_defaults('solve')     # Solve() leaves the tolerances None until the solve (_optimize.py:104-111, 130-136)
         if not velocity.is_staggered:            # CenteredGrid velocity: wide stencil, CG-adaptive only (fluid.py:154-155)
             dims, res, dx = _grid_info(velocity)
             if _fluid._get_obstacles_for(obstacles, velocity) or active is not None or order != 2 or correct_skew or wide_stencil is False \
@@ -86,7 +99,7 @@ def make_incompressible(velocity, obstacles=(), solve=Solve(), active=None, orde
                                                        rel_tol=float(solve.rel_tol), abs_tol=float(solve.abs_tol),
                                                        max_iterations=int(_math.max(solve.max_iterations)), x0=x0)
     except NotEligible as why:
-        return _fall('make_incompressible', why, stock, velocity, obstacles, solve, active, order, correct_skew, wide_stencil)
+        return _fall('make_incompressible', why, stock, velocity, obstacles, original_solve, active, order, correct_skew, wide_stencil)
     pressure = _CenteredGrid(p, _fluid._pressure_extrapolation(velocity.extrapolation), velocity.bounds, velocity.resolution)
     _report(solve, info, pressure)
     return velocity.with_values(values), pressure

@@ -96,6 +96,13 @@ class FakeOps:
                                                  for b in range(dom.batch)]))
 
     @classmethod
+    def mac_cormack_centered(cls, dom, vspec, v, sspec, s, dt, correction_strength=1.0):
+        lower, upper = cls._geom(dom)
+        vc, sc = dom.faces_to_numpy(v, vspec, squeeze=False), dom.centered_to_numpy(s, squeeze=False)
+        return dom.centered_from_numpy(np.stack([O.mac_cormack_centered(sc[b], sspec, [c[b] for c in vc], vspec, lower, upper, dt, correction_strength)
+                                                 for b in range(dom.batch)]))
+
+    @classmethod
     def laplace(cls, dom, spec, x):
         a = dom.centered_to_numpy(x, squeeze=False)
         return dom.centered_from_numpy(np.stack([O.laplace(a[b], dom.dx, spec) for b in range(dom.batch)]))

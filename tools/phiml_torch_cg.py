@@ -100,6 +100,7 @@ def main():
                               "s_per_solve": t_ref, "all_s": all_ref, "iterations": it_ref, "us_per_iteration": 1e6 * t_ref / max(it_ref, 1),
                               "converged": bool(np.asarray(r.converged.cpu())[0])}
         x_ref = r.x[0].float().cpu().numpy()
+        print(json.dumps(out), file=sys.stderr, flush=True)            # partial results survive a later failure
         if args.with_offset:
             offset = O.estimate_matrix_offset(A, n ** 3, np.random.default_rng(0))
             off_t = torch.tensor([offset], dtype=torch.float32, device=dev)
@@ -107,6 +108,7 @@ def main():
             it2 = int(np.asarray(r2.iterations if isinstance(r2.iterations, np.ndarray) else r2.iterations.cpu()).ravel()[0])
             out["phiml_torch_with_matrix_offset"] = {"method": r2.method, "s_per_solve": t2, "all_s": all2, "iterations": it2,
                                                      "us_per_iteration": 1e6 * t2 / max(it2, 1), "matrix_offset": float(offset)}
+    print(json.dumps(out), file=sys.stderr, flush=True)
     if not args.no_ours:
         from phiflow_b200 import _ops as ops
         dom = ops.Domain(res, dx, 1, vbc=vbc)
@@ -124,7 +126,7 @@ def main():
         xr = x_ref - x_ref.mean()
         li = ops.last_launch_info()
         out["phicuda"] = {"s_per_solve": t_our, "all_s": all_our, "iterations": it_our, "us_per_iteration": 1e6 * t_our / max(it_our, 1),
-                          "converged": bool(info['converged'][0]), "kernel": int(li.kernel), "includes": "x.zero_() (one memset) per solve",
+                          "converged": bool(info['converged'][0]), "kernel_variant": li, "includes": "x.zero_() (one memset) per solve",
                           "gbps_at_30B_per_cell_iteration": 30.0 * n ** 3 * it_our / t_our / 1e9}
         out["solutions_max_abs_diff_over_scale"] = float(np.abs((got - got.mean()) - xr).max() / max(np.abs(xr).max(), 1e-30))
         out["speedup_per_solve"] = t_ref / t_our
