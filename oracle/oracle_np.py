@@ -67,10 +67,17 @@ def is_const(side) -> bool:
     return not isinstance(side, str)
 
 
+def kinds_of(bc):
+    """A vector boundary is one spec for all components, or a LIST of `dim` specs when constants differ per component
+    (ConstantExtrapolation of a vector, e.g. the lid `{'y+': vec(x=1, y=0)}` of Lid_Driven_Cavity.ipynb).  The KINDS (constant /
+    ZERO_GRADIENT / PERIODIC per side) are the same in every entry - they decide the stored faces, extrapolation.py:57-62."""
+    return bc[0] if isinstance(bc, list) else bc
+
+
 def valid_outer_faces(bc, axis) -> Tuple[bool, bool]:
     """extrapolation.py:57-62 + determines_boundary_values: ZERO/const -> both determined (:284-285),
     copy pads (ZERO_GRADIENT) -> not determined (:451-452), PERIODIC -> only the upper face (:657-662)."""
-    lo, hi = bc[axis]
+    lo, hi = kinds_of(bc)[axis]
     lo_stored = (lo == ZG) or (lo == PERIODIC)
     hi_stored = (hi == ZG)
     return lo_stored, hi_stored
@@ -79,7 +86,7 @@ def valid_outer_faces(bc, axis) -> Tuple[bool, bool]:
 def is_flexible(bc) -> bool:
     """extrapolation.py:288 (const: False), :565 (ZERO_GRADIENT: True), :665 (PERIODIC: False);
     mixed: any() (:1288-1289)."""
-    return any(side == ZG for ax in bc for side in ax)
+    return any(side == ZG for ax in kinds_of(bc) for side in ax)
 
 
 def pressure_bc(vbc) -> tuple:
@@ -90,7 +97,7 @@ def pressure_bc(vbc) -> tuple:
         if side == ZG:
             return ZERO
         return ZG
-    return tuple((conv(lo), conv(hi)) for lo, hi in vbc)
+    return tuple((conv(lo), conv(hi)) for lo, hi in kinds_of(vbc))
 
 
 def staggered_shapes(res: Sequence[int], vbc) -> List[tuple]:
@@ -430,8 +437,8 @@ def sample_component_on_grid(comp: np.ndarray, c: int, res, vbc_c, target_face_a
 
 
 def component_bcs(vbc, dim):
-    """Per-component boundary of a vector field whose extrapolation does not depend on the component."""
-    return [vbc for _ in range(dim)]
+    """Per-component boundary of a vector field: the same spec for every component, or the given list (see kinds_of)."""
+    return list(vbc) if isinstance(vbc, list) else [vbc for _ in range(dim)]
 
 
 # --------------------------------------------------------------------------------------------------
@@ -440,12 +447,14 @@ def component_bcs(vbc, dim):
 
 def _velocity_at_centers(v, res, vbc):
     d = len(res)
-    return np.stack([sample_component_on_grid(v[c], c, res, vbc, None, vbc) for c in range(d)], -1)
+    comp = component_bcs(vbc, d)
+    return np.stack([sample_component_on_grid(v[c], c, res, comp[c], None, vbc) for c in range(d)], -1)
 
 
 def _velocity_at_faces(v, res, vbc, target_axis, target_vbc):
     d = len(res)
-    return np.stack([sample_component_on_grid(v[c], c, res, vbc, target_axis, target_vbc) for c in range(d)], -1)
+    comp = component_bcs(vbc, d)
+    return np.stack([sample_component_on_grid(v[c], c, res, comp[c], target_axis, target_vbc) for c in range(d)], -1)
 
 
 def semi_lagrangian_centered(s: np.ndarray, sbc, v: List[np.ndarray], vbc, lower, upper, dt: float) -> np.ndarray:
@@ -463,13 +472,14 @@ def semi_lagrangian_staggered(f: List[np.ndarray], fbc, v: List[np.ndarray], vbc
     (self-advection when f is v).  Sample points = stored faces of `f`; velocity there via A10; every component is
     then interpolated on its own staggered sub-grid (reduce_sample, phi/field/_resample.py:66-72, 148-153)."""
     d = len(res)
+    fbc_comp = component_bcs(fbc, d)
     out = []
     for c in range(d):
         v0 = _velocity_at_faces(v, res, vbc, c, fbc)
         lo_c, up_c, res_c = component_grid(lower, upper, res, fbc, c)
         pts = points_of(lo_c, up_c, res_c)
         lookup = (pts + v0 * F32(-dt)).astype(F32)
-        out.append(grid_sample(f[c].astype(F32), to_index_space(lookup, lo_c, up_c, res_c), fbc))
+        out.append(grid_sample(f[c].astype(F32), to_index_space(lookup, lo_c, up_c, res_c), fbc_comp[c]))
     return out
 
 
@@ -679,6 +689,22 @@ def make_incompressible(v: List[np.ndarray], vbc, res, dx, rtol=1e-5, atol=1e-5,
     grad = gradient_faces(p, dx, pbc, vbc)                                       # :158
     v_new = [a - g for a, g in zip(v, grad)]                                     # :161
     return v_new, p, info
+
+
+def diffuse_explicit(u, bc, dx, diffusivity: float, dt: float, substeps: int = 1):
+    """diffuse.explicit, phi/physics/diffuse.py:13-60: `substeps` x  u += amount * laplace(u), amount = diffusivity * (dt / substeps).
+    `u` = centred array with its boundary spec, or a list of staggered components with the vector boundary: the reference's
+    staggered laplace (phi/field/_field_math.py:118-145, `fields = [u]`, math.laplace pads every component of the non-uniform stack
+    by one layer of the component's own boundary) is the per-component laplace - checked against the vendored PhiML in
+    tests/test_staggered_diffusion.py."""
+    amount = F32(diffusivity * (dt / substeps))
+    if isinstance(u, list):
+        comp = component_bcs(bc, len(u))
+        return [diffuse_explicit(a, comp[c], dx, diffusivity, dt, substeps) for c, a in enumerate(u)]
+    u = u.astype(F32)
+    for _ in range(substeps):
+        u = (u + amount * laplace(u, dx, bc)).astype(F32)
+    return u
 
 
 # --------------------------------------------------------------------------------------------------

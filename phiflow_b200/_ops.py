@@ -206,6 +206,33 @@ def laplace_axpy(dom: Domain, bc, x, coeff: float, out=None):
     return out
 
 
+def laplace_axpy_faces(dom: Domain, vbc, v: List[torch.Tensor], coeff: float, substeps: int = 1) -> List[torch.Tensor]:
+    """diffuse.explicit of a STAGGERED field (phi/physics/diffuse.py:13-60 -> phi/field/_field_math.py:118-145 with `fields = [u]`:
+    `math.laplace` of the non-uniform component stack pads every component by one layer of ITS boundary, so component c is an
+    independent array of its stored faces with the boundary spec of component c - verified against the vendored PhiML in
+    tests/test_staggered_diffusion.py).  Not on the north-star path (row N3): composed on the host from the laplace kernel - each
+    component is copied into a centred array of a domain whose resolution is the component's face count (the x component of a
+    walled grid starts at face 1, i.e. 4 bytes off the 16-byte alignment the TMA ring needs), `substeps` x laplace_axpy, copied back."""
+    require_cuda()
+    assert dom.halo == 0, "staggered diffusion is not offered on z-slabs"
+    shapes, offsets = dom.face_shapes(vbc)
+    out = []
+    for c in range(dom.dim):
+        sub = Domain(shapes[c], dom.dx, dom.batch, device=dom.device)
+        spec = vbc[c] if isinstance(vbc, list) else vbc
+        src = (slice(None),) + tuple(slice(offsets[c] if a == c else 0, (offsets[c] if a == c else 0) + shapes[c][a]) for a in range(dom.dim - 1, -1, -1))
+        dst = (slice(None),) + tuple(slice(0, shapes[c][a]) for a in range(dom.dim - 1, -1, -1))
+        a, b = sub.alloc_centered(), sub.alloc_centered()
+        a[dst] = v[c][src]
+        for _ in range(substeps):
+            laplace_axpy(sub, spec, a, coeff, out=b)
+            a, b = b, a
+        res = v[c].clone()
+        res[src] = a[dst]
+        out.append(res)
+    return out
+
+
 def divergence(dom: Domain, vbc, v: List[torch.Tensor], out=None, accessible=None):
     """field.divergence of a staggered grid (phi/field/_field_math.py:617-626); accessible: div *= active mask (fluid.py:138-141)."""
     require_cuda()

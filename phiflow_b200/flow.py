@@ -586,10 +586,13 @@ advect = SimpleNamespace(semi_lagrangian=semi_lagrangian, mac_cormack=mac_cormac
 # ----------------------------------------------------------------------------------------------------------------------
 # diffuse  (phi/physics/diffuse.py)
 # ----------------------------------------------------------------------------------------------------------------------
-def explicit(fld: CenteredGrid, diffusivity: float, dt: float, substeps: int = 1):
-    """diffuse.explicit (phi/physics/diffuse.py:13-60): substeps of  u += (dt/substeps) * diffusivity * laplace(u)."""
-    _require(isinstance(fld, CenteredGrid), "explicit diffusion of staggered fields")
+def explicit(fld, diffusivity: float, dt: float, substeps: int = 1):
+    """diffuse.explicit (phi/physics/diffuse.py:13-60): substeps of  u += (dt/substeps) * diffusivity * laplace(u); for a
+    StaggeredGrid every component is diffused with its own boundary (Lid_Driven_Cavity.ipynb, Variable_Boundaries.ipynb)."""
     amount = float(diffusivity) * float(dt) / substeps
+    if isinstance(fld, StaggeredGrid):
+        return fld.with_values(ops.laplace_axpy_faces(fld.dom, fld.vspec, fld.data, amount, substeps))
+    _require(isinstance(fld, CenteredGrid), "explicit diffusion of this field type")
     data = fld.data
     for _ in range(substeps):
         data = ops.laplace_axpy(fld.dom, fld.spec, data, amount)

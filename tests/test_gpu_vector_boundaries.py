@@ -1,0 +1,168 @@
+"""
+CUDA side of tests/test_vector_boundaries.py: per-component constant boundaries (PhiVBC.comp[c] with different constants - the lid
+`{'y+': vec(x=1, y=0)}` of Lid_Driven_Cavity.ipynb, inflow profiles) through every kernel that reads velocity ghosts, and
+`diffuse.explicit` of a StaggeredGrid, against the oracle (which is pinned for these cases against the vendored PhiML there).
+Then the notebook steps themselves through the phi.flow-like mirror: Lid_Driven_Cavity.ipynb and Variable_Boundaries.ipynb.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle_np as O
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from phiflow_b200 import _ops as ops
+    from phiflow_b200 import flow
+
+EPS = float(np.finfo(np.float32).eps)
+
+VBCS = {
+    'cavity2': [((0.0, 0.0), (0.0, 1.0)), ((0.0, 0.0), (0.0, 0.0))],
+    'inflow2': [((0.5, 'zg'), (0.0, 0.0)), ((-0.25, 'zg'), (0.0, 0.0))],
+    'cavity3': [((0.0, 0.0), (0.0, 1.0), (0.0, 0.0)), ((0.0, 0.0),) * 3, ((0.0, 0.0), (0.0, 0.25), (0.0, 0.0))],
+    'inflow3': [((0.5, 'zg'), (0.0, 0.0), ('periodic', 'periodic')), ((-0.25, 'zg'), (0.0, 0.0), ('periodic', 'periodic')),
+                ((0.125, 'zg'), (0.0, 0.0), ('periodic', 'periodic'))],
+}
+SCALAR = {
+    'zero': lambda d: O.uniform_bc(d, 0.0), 'open': lambda d: O.uniform_bc(d, 'zg'), 'periodic': lambda d: O.uniform_bc(d, 'periodic'),
+    'mixed': lambda d: (('zg', 'zg'), (0.0, 'zg')) + ((('periodic', 'periodic'),) if d == 3 else ()),
+}
+SHAPES = {2: [(37, 22), (130, 9)], 3: [(21, 14, 9)]}
+
+
+def dx_of(d):
+    return (0.5, 0.25) if d == 2 else (0.5, 0.25, 2.0)
+
+
+def rand_staggered(rng, res, vbc, scale=1.0):
+    return [(scale * rng.standard_normal(s)).astype(np.float32) for s in O.staggered_shapes(res, vbc)]
+
+
+def advect_tol(res, arrays):
+    dmax = max(np.abs(np.diff(a, axis=ax)).max() for a in arrays for ax in range(a.ndim) if a.shape[ax] > 1)
+    return 8 * EPS * max(res) * max(dmax, 1e-3) + 4 * EPS * max(np.abs(a).max() for a in arrays)
+
+
+@pytest.mark.parametrize('vname', sorted(VBCS))
+def test_divergence_and_projection(vname):
+    vbc = VBCS[vname]
+    d = len(vbc)
+    rng = np.random.default_rng(1)
+    for res in SHAPES[d]:
+        dx = dx_of(d)
+        dom = ops.Domain(res, dx, 1, vbc=vbc)
+        v = rand_staggered(rng, res, vbc, 0.1)
+        dv = dom.faces_from_numpy(v, vbc)
+        got = dom.centered_to_numpy(ops.divergence(dom, vbc, dv))
+        ref = O.divergence_staggered(v, dx, O.component_bcs(vbc, d))
+        scale = max(np.abs(c).max() for c in v) * sum(2.0 / h for h in dx) + 1.0 / min(dx)
+        np.testing.assert_allclose(got, ref, rtol=0, atol=4 * EPS * scale)
+        prm = ops.cg_params(vbc, rtol=1e-5, atol=1e-5)
+        dv, p = ops.make_incompressible(dom, vbc, dv, None, prm)
+        assert ops.read_results(dom)['converged'][0] == 1
+        v_ref, p_ref, info = O.make_incompressible(v, vbc, res, dx, rtol=1e-5, atol=1e-5, use_matrix_offset=False)
+        out = dom.faces_to_numpy(dv, vbc)
+        for c in range(d):
+            np.testing.assert_allclose(out[c], v_ref[c], rtol=0, atol=2e-4 * max(np.abs(v_ref[c]).max(), 1e-2))
+        div = dom.centered_to_numpy(ops.divergence(dom, vbc, dv))
+        assert np.abs(div).max() < max(5e-5, 1e-4 * scale)
+
+
+@pytest.mark.parametrize('vname', sorted(VBCS))
+def test_advection_reads_per_component_ghosts(vname):
+    """Back-traces leave the domain through the lid / inflow side: the sampled velocity and the advected component there come from
+    the constants of THAT component."""
+    vbc = VBCS[vname]
+    d = len(vbc)
+    rng = np.random.default_rng(2)
+    res = SHAPES[d][0]
+    dx = dx_of(d)
+    lower, upper = tuple(0.0 for _ in res), tuple(r * h for r, h in zip(res, dx))
+    dom = ops.Domain(res, dx, 1, vbc=vbc)
+    v = rand_staggered(rng, res, vbc, 1.3)
+    dv = dom.faces_from_numpy(v, vbc)
+    dt = 0.6
+    got = dom.faces_to_numpy(ops.advect_staggered(dom, vbc, dv, vbc, dv, dt), vbc)
+    ref = O.semi_lagrangian_staggered(v, vbc, v, vbc, res, lower, upper, dt)
+    tol = advect_tol(res, v) + 8 * EPS * max(res)             # + the unit jumps to the boundary constants
+    for c in range(d):
+        np.testing.assert_allclose(got[c], ref[c], rtol=0, atol=tol)
+    s = rng.standard_normal(res).astype(np.float32)
+    sbc = O.uniform_bc(d, 'zg')
+    got_s = dom.centered_to_numpy(ops.advect_centered(dom, vbc, dv, sbc, dom.centered_from_numpy(s), dt))
+    np.testing.assert_allclose(got_s, O.semi_lagrangian_centered(s, sbc, v, vbc, lower, upper, dt), rtol=0, atol=advect_tol(res, [s]))
+    got_mc = dom.centered_to_numpy(ops.mac_cormack_centered(dom, vbc, dv, sbc, dom.centered_from_numpy(s), dt))
+    np.testing.assert_allclose(got_mc, O.mac_cormack_centered(s, sbc, v, vbc, lower, upper, dt), rtol=0, atol=4 * advect_tol(res, [s]))
+
+
+@pytest.mark.parametrize('substeps', [1, 3])
+@pytest.mark.parametrize('vname', sorted(VBCS) + ['zero', 'open', 'periodic', 'mixed'])
+def test_staggered_diffusion(vname, substeps):
+    """diffuse.explicit(StaggeredGrid): every component diffused with its own boundary (oracle == vendored PhiML, CPU test)."""
+    for d in ((2, 3) if vname in SCALAR else (len(VBCS[vname]),)):
+        vbc = SCALAR[vname](d) if vname in SCALAR else VBCS[vname]
+        rng = np.random.default_rng(3)
+        for res in SHAPES[d]:
+            dx = dx_of(d)
+            dom = ops.Domain(res, dx, 2, vbc=vbc)
+            v = [np.stack([a, -0.5 * a]) for a in rand_staggered(rng, res, vbc)]
+            dv = dom.faces_from_numpy(v, vbc)
+            before = [t.clone() for t in dv]
+            amount = 0.01 * (0.5 / substeps)
+            out = dom.faces_to_numpy(ops.laplace_axpy_faces(dom, vbc, dv, amount, substeps), vbc, squeeze=False)
+            for c in range(d):
+                assert torch.equal(dv[c], before[c])                              # out of place
+                for b in range(2):
+                    ref = O.diffuse_explicit(v[c][b], O.component_bcs(vbc, d)[c], dx, 0.01, 0.5, substeps)
+                    scale = (np.abs(v[c]).max() + 1.0) * (1 + amount * sum(4.0 / h ** 2 for h in dx))
+                    np.testing.assert_allclose(out[c][b], ref, rtol=0, atol=16 * EPS * scale * substeps)      # a wrong ghost would show as ~amount/h^2 = 1e-2
+
+
+def test_lid_driven_cavity_notebook_step():
+    """examples/grids/Lid_Driven_Cavity.ipynb: boundary = {'x': 0, 'y-': 0, 'y+': vec(x=1, y=0)}, v0 = StaggeredGrid(0, boundary, x=50, y=32),
+    step = semi_lagrangian -> diffuse.explicit(v, 0.1, dt) -> make_incompressible(v, solve=Solve(x0=p)).  Mirror API vs the oracle."""
+    boundary = {'x': 0, 'y-': 0, 'y+': (1.0, 0.0)}
+    v = flow.StaggeredGrid(0, boundary, x=50, y=32)
+    assert isinstance(v.vspec, list)
+    res, dx, lower, upper = (50, 32), (1.0, 1.0), (0.0, 0.0), (50.0, 32.0)
+    vspec = [((0.0, 0.0), (0.0, 1.0)), ((0.0, 0.0), (0.0, 0.0))]
+    ref = [np.zeros(s, np.float32) for s in O.staggered_shapes(res, vspec)]
+    p, p_ref = None, None
+    for _ in range(6):
+        v = flow.advect.semi_lagrangian(v, v, 1.0)
+        v = flow.diffuse.explicit(v, 0.1, 1.0)
+        v, p = flow.fluid.make_incompressible(v, solve=flow.Solve('CG', 1e-5, 1e-5, x0=p))
+        ref = O.semi_lagrangian_staggered(ref, vspec, ref, vspec, res, lower, upper, 1.0)
+        ref = O.diffuse_explicit(ref, vspec, dx, 0.1, 1.0)
+        ref, p_ref, info = O.make_incompressible(ref, vspec, res, dx, rtol=1e-5, atol=1e-5, x0=p_ref, use_matrix_offset=False)
+    got = v.numpy()
+    assert float(np.abs(ref[0]).max()) > 0.05                                  # the lid drives a vortex
+    for c in range(2):
+        np.testing.assert_allclose(got[c][0] if got[c].ndim == 3 else got[c], ref[c], rtol=0, atol=2e-4)
+    div = flow.field.divergence(v).numpy()
+    assert float(np.abs(div).max()) < 1e-4
+
+
+def test_variable_boundaries_notebook_step():
+    """examples/grids/Variable_Boundaries.ipynb with a uniform inflow profile: boundary = {'x-': vec(x=0.5, y=0), 'x+': ZERO_GRADIENT, 'y': 0}
+    (the notebook's tanh profile is a FieldEmbedding boundary - outside the fast path, it falls through to stock PhiFlow)."""
+    boundary = {'x-': (0.5, 0.0), 'x+': flow.ZERO_GRADIENT, 'y': 0}
+    v = flow.StaggeredGrid(0, boundary, flow.Box(x=10, y=10), x=50, y=32)
+    res, dx, lower, upper = (50, 32), (0.2, 10.0 / 32), (0.0, 0.0), (10.0, 10.0)
+    vspec = [((0.5, 'zg'), (0.0, 0.0)), ((0.0, 'zg'), (0.0, 0.0))]
+    assert v.vspec == vspec
+    ref = [np.zeros(s, np.float32) for s in O.staggered_shapes(res, vspec)]
+    p, p_ref = None, None
+    for _ in range(3):
+        v = flow.advect.semi_lagrangian(v, v, 1.0)
+        v = flow.diffuse.explicit(v, 0.01, 1.0)
+        v, p = flow.fluid.make_incompressible(v, solve=flow.Solve('CG', 1e-5, 1e-5, x0=p))
+        ref = O.semi_lagrangian_staggered(ref, vspec, ref, vspec, res, lower, upper, 1.0)
+        ref = O.diffuse_explicit(ref, vspec, dx, 0.01, 1.0)
+        ref, p_ref, info = O.make_incompressible(ref, vspec, res, dx, rtol=1e-5, atol=1e-5, x0=p_ref, use_matrix_offset=False)
+    got = v.numpy()
+    assert float(np.abs(ref[0]).max()) > 0.1
+    for c in range(2):
+        np.testing.assert_allclose(got[c][0] if got[c].ndim == 3 else got[c], ref[c], rtol=0, atol=5e-4)
