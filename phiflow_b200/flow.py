@@ -21,7 +21,7 @@ from . import _ops as ops
 from . import field_io
 from . import scene as _scene
 
-__all__ = ['Scene', 'Box', 'Sphere', 'CenteredGrid', 'StaggeredGrid', 'extrapolation', 'ZERO', 'ONE', 'PERIODIC', 'ZERO_GRADIENT',
+__all__ = ['Scene', 'vec', 'Box', 'Sphere', 'CenteredGrid', 'StaggeredGrid', 'extrapolation', 'ZERO', 'ONE', 'PERIODIC', 'ZERO_GRADIENT',
            'BOUNDARY', 'combine_sides', 'Solve', 'SolveTape', 'NotConverged', 'Diverged', 'ConvergenceException', 'field',
            'resample', 'advect', 'diffuse', 'fluid', 'math', 'write', 'read']
 
@@ -71,6 +71,12 @@ class Extrapolation:
 
     def __repr__(self):
         return f"Extrapolation({self.default}, {self.sides})"
+
+
+def vec(**components):
+    """phiml.math.vec(x=1, y=0) as this mirror spells vectors: a tuple in axis order (boundary constants, buoyancy factors)."""
+    assert tuple(components) == tuple(AXES[:len(components)]), f"components must be {AXES[:len(components)]} in order"
+    return tuple(float(v) for v in components.values())
 
 
 def ConstantExtrapolation(value):
