@@ -70,8 +70,11 @@ def test_divergence_and_projection(vname):
         out = dom.faces_to_numpy(dv, vbc)
         for c in range(d):
             np.testing.assert_allclose(out[c], v_ref[c], rtol=0, atol=1e-3 * max(np.abs(v_ref[c]).max(), 0.1))
+        # fp32 floor of the projection: with the inflow driving a pressure of ~32 on the 130 x 9 grid the reference arithmetic itself
+        # leaves max|div| = 9.5e-4 (oracle, rtol 1e-5 and 1e-6 alike); the CUDA path measured 9.7e-4.  The bar is the oracle's own.
         div = dom.centered_to_numpy(ops.divergence(dom, vbc, dv))
-        assert np.abs(div).max() < max(5e-5, 1e-4 * scale)
+        div_ref = O.divergence_staggered(v_ref, dx, O.component_bcs(vbc, d))
+        assert np.abs(div).max() < max(5e-5, 1e-4 * scale, 2 * float(np.abs(div_ref).max()) + 5e-5)
 
 
 @pytest.mark.parametrize('vname', sorted(VBCS))
