@@ -27,111 +27,7 @@ from phiflow_b200 import _ops  # noqa: E402
 from phiflow_b200.phi_cuda import _adapter as A  # noqa: E402
 
 
-# ---- oracle-backed stand-in for phiflow_b200._ops (CPU tensors in the device layout) -------------------------------------
-class FakeOps:
-    Domain = _ops.Domain
-    cg_params = staticmethod(_ops.cg_params)
-    last = None
-
-    @staticmethod
-    def _geom(dom):
-        lower = (0.0,) * dom.dim
-        upper = tuple(dom.res[a] * dom.dx[a] for a in range(dom.dim))
-        return lower, upper
-
-    @classmethod
-    def make_incompressible(cls, dom, vspec, v, p, prm):
-        comps = dom.faces_to_numpy(v, vspec, squeeze=False)
-        p0 = dom.centered_to_numpy(p, squeeze=False)
-        outs, ps, infos = [], [], []
-        solver = O.cg_adaptive if prm.method == 1 else O.cg
-        for b in range(dom.batch):
-            vb = [c[b] for c in comps]
-            # same sequence as oracle.make_incompressible, with the solver the engine was asked for
-            div = O.divergence_staggered(vb, dom.dx, O.component_bcs(vspec, dom.dim))
-            if not O.is_flexible(vspec):
-                div = div - np.mean(div, dtype=np.float32)
-            Amat = O.poisson_matrix(dom.res, dom.dx, O.pressure_bc(vspec))
-            info = solver(Amat, div, p0[b], prm.rtol, prm.atol, prm.max_iter, None)
-            pb = info['x'].reshape(dom.res)
-            grad = O.gradient_faces(pb, dom.dx, O.pressure_bc(vspec), vspec)
-            outs.append([a - g for a, g in zip(vb, grad)]); ps.append(pb); infos.append(info)
-        new = dom.faces_from_numpy([np.stack([o[c] for o in outs]) for c in range(dom.dim)], vspec)
-        for c in range(dom.dim):
-            v[c].copy_(new[c])
-        p.copy_(dom.centered_from_numpy(np.stack(ps)))
-        rec = np.zeros(dom.batch, dtype=_ops._RESULT_DTYPE)
-        for b, info in enumerate(infos):
-            rec[b] = (info['iterations'], int(info['converged']), int(info['diverged']), info['residual_sq'], info['tol_sq'], 0.0)
-        cls.last = rec
-
-    @classmethod
-    def make_incompressible_centered(cls, dom, vspec, v, p, rtol=1e-5, atol=1e-5, max_iter=1000, matrix_offset=None):
-        comps = [dom.centered_to_numpy(t, squeeze=False) for t in v]
-        outs, ps, rec = [], [], np.zeros(dom.batch, dtype=_ops._RESULT_DTYPE)
-        for b in range(dom.batch):
-            vb, pb, info = O.make_incompressible_centered([c[b] for c in comps], vspec, dom.res, dom.dx, rtol, atol, max_iter)
-            outs.append(vb); ps.append(pb)
-            rec[b] = (info['iterations'], int(info['converged']), int(info['diverged']), info['residual_sq'], info['tol_sq'], 0.0)
-        cls.last = rec
-        new = [dom.centered_from_numpy(np.stack([o[c] for o in outs])) for c in range(dom.dim)]
-        return new, dom.centered_from_numpy(np.stack(ps))
-
-    @classmethod
-    def read_results(cls, dom):
-        return cls.last
-
-    @classmethod
-    def advect_staggered(cls, dom, vspec, v, fspec, f, dt):
-        lower, upper = cls._geom(dom)
-        vc, fc = dom.faces_to_numpy(v, vspec, squeeze=False), dom.faces_to_numpy(f, fspec, squeeze=False)
-        out = [O.semi_lagrangian_staggered([c[b] for c in fc], fspec, [c[b] for c in vc], vspec, dom.res, lower, upper, dt) for b in range(dom.batch)]
-        return dom.faces_from_numpy([np.stack([o[c] for o in out]) for c in range(dom.dim)], fspec)
-
-    @classmethod
-    def advect_centered(cls, dom, vspec, v, sspec, s, dt):
-        lower, upper = cls._geom(dom)
-        vc, sc = dom.faces_to_numpy(v, vspec, squeeze=False), dom.centered_to_numpy(s, squeeze=False)
-        return dom.centered_from_numpy(np.stack([O.semi_lagrangian_centered(sc[b], sspec, [c[b] for c in vc], vspec, lower, upper, dt)
-                                                 for b in range(dom.batch)]))
-
-    @classmethod
-    def mac_cormack_centered(cls, dom, vspec, v, sspec, s, dt, correction_strength=1.0):
-        lower, upper = cls._geom(dom)
-        vc, sc = dom.faces_to_numpy(v, vspec, squeeze=False), dom.centered_to_numpy(s, squeeze=False)
-        return dom.centered_from_numpy(np.stack([O.mac_cormack_centered(sc[b], sspec, [c[b] for c in vc], vspec, lower, upper, dt, correction_strength)
-                                                 for b in range(dom.batch)]))
-
-    @classmethod
-    def laplace(cls, dom, spec, x):
-        a = dom.centered_to_numpy(x, squeeze=False)
-        return dom.centered_from_numpy(np.stack([O.laplace(a[b], dom.dx, spec) for b in range(dom.batch)]))
-
-    @classmethod
-    def grid_sample(cls, dom, bc, grid, coords):
-        g = dom.centered_to_numpy(grid, squeeze=False)                     # (batch, x, y[, z])
-        c = coords.numpy()
-        return torch.from_numpy(np.stack([O.grid_sample(g[b], c[b], bc) for b in range(dom.batch)]).astype(np.float32))
-
-    @classmethod
-    def cg_poisson(cls, dom, vspec, rhs, x, prm):
-        y, x0 = dom.centered_to_numpy(rhs, squeeze=False), dom.centered_to_numpy(x, squeeze=False)
-        Amat = O.poisson_matrix(dom.res, dom.dx, O.pressure_bc(vspec))
-        solver = O.cg_adaptive if prm.method == 1 else O.cg
-        rec, xs = np.zeros(dom.batch, dtype=_ops._RESULT_DTYPE), []
-        for b in range(dom.batch):
-            info = solver(Amat, y[b], x0[b], prm.rtol, prm.atol, prm.max_iter, None)
-            xs.append(info['x'].reshape(dom.res))
-            rec[b] = (info['iterations'], int(info['converged']), int(info['diverged']), info['residual_sq'], info['tol_sq'], 0.0)
-        cls.last = rec
-        x.copy_(dom.centered_from_numpy(np.stack(xs)))
-        return x
-
-    @classmethod
-    def divergence(cls, dom, vspec, v):
-        vc = dom.faces_to_numpy(v, vspec, squeeze=False)
-        return dom.centered_from_numpy(np.stack([O.divergence_staggered([c[b] for c in vc], dom.dx, O.component_bcs(vspec, dom.dim))
-                                                 for b in range(dom.batch)]))
+from oracle_engine import OracleEngine as FakeOps  # noqa: E402  (oracle-backed stand-in for phiflow_b200._ops, CPU tensors in the device layout)
 
 
 @pytest.fixture()
