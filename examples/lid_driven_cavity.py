@@ -9,6 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from phiflow_b200.flow import *  # noqa: E402,F401,F403
 
 
+@jit_compile
 def step(v, p, dt=1., viscosity=.1):
     v = advect.semi_lagrangian(v, v, dt)
     v = diffuse.explicit(v, viscosity, dt)
@@ -18,10 +19,8 @@ def step(v, p, dt=1., viscosity=.1):
 
 def main(steps=300, x=50, y=32):
     boundary = {'x': 0, 'y-': 0, 'y+': vec(x=1, y=0)}
-    v = StaggeredGrid(0, boundary, x=x, y=y)
-    p = None
-    for _ in range(steps):
-        v, p = step(v, p)
+    v0 = StaggeredGrid(0, boundary, x=x, y=y)
+    v, p = iterate(step, steps, v0, None)           # the notebook records the trajectory: iterate(step, batch(time=300), v0, None)
     vx, vy = v.numpy()
     print(f"lid-driven cavity {x}x{y}, {steps} steps: max|v_x| = {float(np.abs(vx).max()):.4f} (lid speed 1), "
           f"return flow min v_x = {float(vx.min()):.4f}, max|div v| = {float(np.abs(field.divergence(v).numpy()).max()):.2e}")

@@ -11,6 +11,7 @@ Fields hold device tensors in the library layout; `.numpy(
 Anything outside the fast path raises NotImplementedError (where the reference-side façade would fall through to stock
 PhiFlow).  No CPU fallback.
 """
+from builtins import range as builtins_range
 from types import SimpleNamespace
 from typing import Sequence
 
@@ -21,7 +22,7 @@ from . import _ops as ops
 from . import field_io
 from . import scene as _scene
 
-__all__ = ['Scene', 'vec', 'Box', 'Sphere', 'CenteredGrid', 'StaggeredGrid', 'extrapolation', 'ZERO', 'ONE', 'PERIODIC', 'ZERO_GRADIENT',
+__all__ = ['Scene', 'vec', 'batch', 'iterate', 'jit_compile', 'Box', 'Sphere', 'CenteredGrid', 'StaggeredGrid', 'extrapolation', 'ZERO', 'ONE', 'PERIODIC', 'ZERO_GRADIENT',
            'BOUNDARY', 'combine_sides', 'Solve', 'SolveTape', 'NotConverged', 'Diverged', 'ConvergenceException', 'field',
            'resample', 'advect', 'diffuse', 'fluid', 'math', 'write', 'read']
 
@@ -229,6 +230,39 @@ class SolveTape:
 
 math = SimpleNamespace(Solve=Solve, SolveTape=SolveTape, NotConverged=NotConverged, Diverged=Diverged,
                        ConvergenceException=ConvergenceException, extrapolation=extrapolation)
+
+
+def jit_compile(f=None, **_):
+    """math.jit_compile (PhiML/phiml/math/_functional.py): the identity here - every call already is a pre-compiled CUDA kernel behind
+    the C ABI, and ctypes launches must not be traced."""
+    return f if f is not None else (lambda g: g)
+
+
+def batch(**dims):
+    """batch(time=300) as `iterate` uses it: the name and length of the trajectory dimension."""
+    assert len(dims) == 1, "one trajectory dimension"
+    return dict(dims)
+
+
+def iterate(f, iterations, *x0, f_kwargs: dict = None, range=range, substeps: int = 1, **f_kwargs_):
+    """math.iterate (PhiML/phiml/math/_functional.py:1241-1300): calls `x = f(*x, **kwargs)` repeatedly.  `iterations` = int -> the final
+    state; = batch(time=N) -> one trajectory per state variable, as a LIST of N + 1 entries starting with the initial state (the
+    reference stacks them along the batch dim; stacked device trajectories of 3-D runs do not fit, lists of Fields do the same job).
+    `substeps` calls of f separate two recorded entries."""
+    kwargs = dict(f_kwargs or {}, **f_kwargs_)
+    x = tuple(x0)
+    record = isinstance(iterations, dict)
+    n = int(next(iter(iterations.values()))) if record else int(iterations)
+    trj = [[xi] for xi in x] if record else None
+    for _ in range(n):
+        for _ in builtins_range(substeps):
+            out = f(*x[:len(x0)], **kwargs)
+            x = tuple(out) if isinstance(out, (tuple, list)) else (out,)
+        if record:
+            for t, xi in zip(trj, x):
+                t.append(xi)
+    result = tuple(trj) if record else x
+    return result if len(result) > 1 else result[0]
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -121,3 +121,27 @@ def test_batched_smoke_obstacle_example(F):
     vx = v.numpy()[0]
     inside = F.Box(x=(35, 65), y=(50, 70)).lies_inside(v.face_points(0))
     assert float(np.abs(vx[:, inside]).max()) < 1e-5
+
+
+def test_iterate_and_jit_compile_like_the_notebooks(F):
+    """Lid_Driven_Cavity.ipynb as written: `@jit_compile def step(v, p, dt=1., viscosity=.1)` and
+    `v_trj, p_trj = iterate(step, batch(time=4), v0, None)` (math.iterate, PhiML/phiml/math/_functional.py:1241-1300)."""
+    @F.jit_compile
+    def step(v, p, dt=1., viscosity=.1):
+        v = F.advect.semi_lagrangian(v, v, dt)
+        v = F.diffuse.explicit(v, viscosity, dt)
+        v, p = F.fluid.make_incompressible(v, solve=F.Solve(x0=p))
+        return v, p
+
+    v0 = F.StaggeredGrid(0, {'x': 0, 'y-': 0, 'y+': F.vec(x=1, y=0)}, x=16, y=12)
+    v_trj, p_trj = F.iterate(step, F.batch(time=4), v0, None)
+    assert len(v_trj) == 5 and v_trj[0] is v0 and p_trj[0] is None
+    v_end, p_end = F.iterate(step, 4, v0, None)
+    for a, b in zip(v_trj[-1].numpy(), v_end.numpy()):
+        np.testing.assert_array_equal(a, b)
+    # substeps: two calls per recorded entry; keyword arguments reach the step
+    v_sub, _ = F.iterate(step, F.batch(time=2), v0, None, substeps=2, dt=1.)
+    for a, b in zip(v_sub[-1].numpy(), v_end.numpy()):
+        np.testing.assert_array_equal(a, b)
+    calls = []
+    assert F.iterate(lambda x: calls.append(x) or x + 1, 3, 0, range=lambda n: range(n)) == 3 and calls == [0, 1, 2]
