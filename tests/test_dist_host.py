@@ -1,6 +1,6 @@
 """
 Host-side logic of the multi-GPU path on CPU: slab geometry, boundary rewriting and the halo exchange, run with
-world_size 2 and 3 over gloo.  The kernels themselves are covered by tools/dist_check.py on GPUs.
+world_size 2 and 3 over gloo.  The kernels themselves are covered by tests/tools/dist_check.py on GPUs.
 """
 import os
 import socket

@@ -2,7 +2,7 @@
 PHI_BC_HALO (z-slab sides that border another rank) on ONE GPU: a periodic grid is run once with PERIODIC z sides and once as
 a "slab" whose halo planes hold the wrapped neighbour planes, exactly what the halo exchange of phiflow_b200.dist delivers.
 Every kernel that reads across a slab face must give bit-identical owned planes in both runs (the multi-GPU parity proper is
-tools/dist_check.py / tests/test_gpu_dist.py, which need >= 2 GPUs).
+tests/tools/dist_check.py / tests/test_gpu_dist.py, which need >= 2 GPUs).
 """
 import numpy as np
 import pytest

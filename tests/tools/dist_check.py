@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """
-Multi-GPU parity check:  torchrun --nproc-per-node N tools/dist_check.py
+Multi-GPU parity check:  torchrun --nproc-per-node N tests/tools/dist_check.py
 Every rank runs its z-slab of a small plume; rank 0 additionally runs the whole grid on its own GPU with the
 single-GPU kernels, and the gathered slab results must agree with it (the distributed solve only changes the order of
 the dot-product reductions).
@@ -12,7 +12,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from phiflow_b200 import _ops as ops  # noqa: E402
 from phiflow_b200.dist import Slab, SlabPlume  # noqa: E402
 

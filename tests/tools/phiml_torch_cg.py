@@ -13,7 +13,7 @@ torch-CUDA backend on the same B200 for C2"): the pressure solve of the 256^3 pe
 the part that can, and it is the part that matters.  Timing: CUDA events, 1 warm-up + `--reps` solves each, device synchronised on
 both sides.  Prints one JSON line (committed as profiles/r2_phiml_torch_cg.json).
 
-    python tools/phiml_torch_cg.py [--n 256] [--reps 3] [--with-offset] [--no-ours]
+    python tests/tools/phiml_torch_cg.py [--n 256] [--reps 3] [--with-offset] [--no-ours]
 """
 import argparse
 import json
@@ -25,7 +25,7 @@ import warnings
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 REF = os.path.join(ROOT, 'baseline', '_ref')
 
